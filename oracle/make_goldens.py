@@ -1,0 +1,164 @@
+"""Generate ``tests/golden/*.npz`` by EXECUTING THE REFERENCE (build container only).
+
+    python -m oracle.make_goldens            # from the repo root; needs /root/reference
+
+The reference ships no golden vectors, so these fixtures are the pin for
+``oracle/restate_np.py`` and ``oracle/port_torch.py`` and, through them, for the CUDA path.
+Inputs and weights are NOT stored: they are regenerated from seeds by ``oracle/synth.py``
+(numpy PCG64, platform-stable); a checksum of each is stored to detect drift.
+
+What is captured, per case, from the unmodified ``LunaTokis.decoding``
+(``Sakuya_arch_test.py:364-459``) via forward hooks on its three SIREN sub-modules:
+  * the full 201/263/525-wide MLP inputs at a strided subset of queries -- these contain the
+    nearest-gathered latents, ``rel_coord``, the bilinear gathers and the warped gathers,
+    i.e. every intermediate of stages A-D;
+  * HRfeat / flow at the same subset, the full RGB output;
+and separately the per-axis nearest-index tables of ``F.grid_sample(mode='nearest')`` and the
+``make_coord`` axes for every (n_lr, n_hr) pair the configs use.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+from oracle import synth  # noqa: E402
+from oracle.ref_loader import build_reference_model, clear_warp_cache, load_reference_module  # noqa: E402
+
+ROWS = 200  # about this many sampled queries per case in the stage dumps
+
+CASES = {
+    # name: dict(B,H,W,scale,times,wseed,stress,iseed,latent_std)
+    "x4_init": dict(B=1, H=16, W=16, scale=None, times=[0.0, 0.375], wseed=0, stress=False, iseed=0, latent_std=0.05),
+    "x6p5_stress": dict(B=1, H=16, W=16, scale=(104, 104), times=[1 / 9, 8 / 9], wseed=1, stress=True, iseed=1,
+                        latent_std=0.05),
+    "odd_b2_stress": dict(B=2, H=12, W=10, scale=(37, 53), times=[[0.25, 0.75]], wseed=2, stress=True, iseed=2,
+                          latent_std=1.0),
+    "down_stress": dict(B=1, H=20, W=24, scale=(13, 17), times=[0.5], wseed=3, stress=True, iseed=3, latent_std=0.3),
+}
+
+AXIS_PAIRS = [(64, 256), (64, 416), (270, 1080), (270, 1755), (480, 1920), (480, 3120), (540, 2160),
+              (960, 3840), (272, 1088), (10, 37), (12, 53), (16, 64), (16, 104), (20, 13), (24, 17), (7, 7)]
+
+
+def checksum(*arrays) -> float:
+    return float(sum(np.abs(np.asarray(a, dtype=np.float64)).sum() for a in arrays))
+
+
+def run_case(name: str, cfg: dict) -> dict:
+    import torch
+
+    weights = synth.make_weights(cfg["wseed"], cfg["stress"])
+    latent, frames = synth.make_inputs(cfg["iseed"], cfg["B"], cfg["H"], cfg["W"], cfg["latent_std"])
+    model = build_reference_model(weights)
+    clear_warp_cache()
+    model.feat = torch.from_numpy(latent)
+    model.inp = torch.from_numpy(frames)
+    B = cfg["B"]
+    tm = np.asarray(cfg["times"], dtype=np.float32)
+    if tm.ndim == 1:
+        times = [torch.tensor([[float(t)]], dtype=torch.float32) for t in tm]       # [1,1] (custom_video_test.py:50)
+    else:
+        times = [torch.tensor(row, dtype=torch.float32).view(B, 1) for row in tm]   # [B,1] (VideoSR_base_model.py:93)
+    cap = {"feat_imnet": [], "flow_imnet": [], "encode_imnet": []}
+    hooks = []
+    for net in cap:
+        def hook(mod, inp, out, net=net):
+            cap[net].append((inp[0].detach().numpy().copy(), out.detach().numpy().copy()))
+        hooks.append(getattr(model, net).register_forward_hook(hook))
+    with torch.no_grad():
+        preds = model.decoding(times, cfg["scale"])
+    for h in hooks:
+        h.remove()
+    rgb = np.stack([p.numpy() for p in preds], 0)                                   # [T,B,3,HH,WW]
+    T = len(times)
+    HH, WW = rgb.shape[-2:]
+    Q = HH * WW
+    sel = np.arange(0, B * Q, max(1, (B * Q // ROWS)) | 1)
+    out = {"rgb": rgb.astype(np.float32), "sel": sel.astype(np.int64),
+           "input_checksum": np.float64(checksum(latent, frames)),
+           "weight_checksum": np.float64(checksum(*weights.values()))}
+    for c in range(T):
+        out[f"feat_in_{c}"] = cap["feat_imnet"][c][0][sel]
+        out[f"hr_{c}"] = cap["feat_imnet"][c][1][sel]
+        out[f"flow_in_{c}"] = cap["flow_imnet"][c][0][sel]
+        out[f"flow_{c}"] = cap["flow_imnet"][c][1]                                  # full [B*Q,4]
+        out[f"enc_in_{c}"] = cap["encode_imnet"][c][0][sel]
+    # sibling methods (same building blocks) where applicable
+    if B == 1 and tm.ndim == 1:
+        tl = [float(t) for t in tm]
+        with torch.no_grad():
+            clear_warp_cache()
+            fast = model.decoding_fasttest(tl, cfg["scale"])
+            clear_warp_cache()
+            ens = model.decoding_localensemble(tl, cfg["scale"])
+        out["rgb_fasttest"] = fast.numpy().astype(np.float32)
+        out["rgb_localensemble"] = ens.numpy().astype(np.float32)
+    return out
+
+
+def run_config1(stress: bool) -> dict:
+    """Config 1 of BASELINE.json (64x64 latent -> 256x256, 8 timesteps): store a strided sample."""
+    import torch
+
+    weights = synth.make_weights(0, stress)
+    latent, frames = synth.make_inputs(0, 1, 64, 64, 0.05)
+    model = build_reference_model(weights)
+    clear_warp_cache()
+    model.feat = torch.from_numpy(latent)
+    model.inp = torch.from_numpy(frames)
+    times = [torch.tensor([[i / 8.0]], dtype=torch.float32) for i in range(8)]
+    with torch.no_grad():
+        preds = model.decoding(times, None)
+    rgb = np.stack([p.numpy() for p in preds], 0)                                   # [8,1,3,256,256]
+    return {"rgb_sub": rgb[:, :, :, 1::5, 2::5].astype(np.float32),
+            "mean": rgb.mean(axis=(1, 2, 3, 4)).astype(np.float64),
+            "absmax": np.abs(rgb).max(axis=(1, 2, 3, 4)).astype(np.float64),
+            "input_checksum": np.float64(checksum(latent, frames)),
+            "weight_checksum": np.float64(checksum(*weights.values()))}
+
+
+def axis_goldens() -> dict:
+    """Per-axis nearest indices straight from ``F.grid_sample(mode='nearest')`` on an index ramp,
+    the ``make_coord`` axes and ``torch.linspace`` for every (n_lr, n_hr) pair."""
+    import torch
+    import torch.nn.functional as F
+
+    sat = load_reference_module()
+    out = {"pairs": np.asarray(AXIS_PAIRS, dtype=np.int64)}
+    for n_lr, n_hr in AXIS_PAIRS:
+        c = sat.make_coord((n_hr, 1)).clamp(-1 + 1e-6, 1 - 1e-6)                    # [n_hr,2] (y, x=0)
+        ramp = torch.arange(n_lr, dtype=torch.float32).view(1, 1, n_lr, 1)           # value == row index
+        g = c.flip(-1).view(1, 1, n_hr, 2)
+        idx = F.grid_sample(ramp, g, mode="nearest", align_corners=False).view(-1)
+        lr_c = sat.make_coord((n_lr, 1), flatten=False)[:, 0, 0]
+        out[f"idx_{n_lr}_{n_hr}"] = idx.numpy().astype(np.int32)
+        out[f"coord_{n_hr}"] = c[:, 0].numpy().astype(np.float32)
+        out[f"coord_{n_lr}"] = sat.make_coord((n_lr, 1)).clamp(-1 + 1e-6, 1 - 1e-6)[:, 0].numpy().astype(np.float32)
+        out[f"lrcoord_{n_lr}"] = lr_c.numpy().astype(np.float32)
+        out[f"linspace_{n_hr}"] = torch.linspace(-1.0, 1.0, n_hr).numpy().astype(np.float32)
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    for name, cfg in CASES.items():
+        res = run_case(name, cfg)
+        np.savez_compressed(os.path.join(GOLD, f"case_{name}.npz"), **res)
+        print(name, {k: getattr(v, "shape", None) for k, v in res.items() if k.startswith("rgb")})
+    for stress in (False, True):
+        res = run_config1(stress)
+        np.savez_compressed(os.path.join(GOLD, f"config1_{'stress' if stress else 'init'}.npz"), **res)
+        print("config1", stress, res["absmax"])
+    np.savez_compressed(os.path.join(GOLD, "axis_tables.npz"), **axis_goldens())
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
