@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- decoded space-time queries/s of the STIF query decoder on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode bf16|fp32] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic input: BASELINE.json config 2
+(x4 spatial / x2 temporal decode of a 480x270 latent to 1080p: B=1, H=270, W=480 -> 1080x1920,
+times [0, 0.5]; 4 147 200 queries = K0 latent projection + 2 x (K1 stage A+B, K2 stage C+D+E)).
+At N>1 every rank decodes its own frame pair of that shape (the path shards by (pair, t) slabs,
+SURVEY.md section 8e): weak scaling, no collective inside the decode loop; the MLP weights are
+broadcast once from rank 0 over NCCL before the timed region.
+
+One JSON line is printed by rank 0 (see the keys at the bottom).  Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "stif-continuous-video-representation_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+FLOP_PER_QUERY = 416_896            # 2 x 208 448 MAC, unpadded
+FLOP_K1 = 2 * (49_728 + 38_336)     # feat_imnet + flow_imnet  (stage A+B)
+FLOP_K2 = 2 * 120_384               # encode_imnet              (stage E)
+WORKLOADS = {
+    # name: (H, W, HH, WW, times)
+    "config2": (270, 480, 1080, 1920, [0.0, 0.5]),
+    "config1": (64, 64, 256, 256, [i / 8.0 for i in range(8)]),
+    "config4_slab": (540, 960, 2160, 3840, [0.375]),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for (ts, r) in self.rows if t0 - 0.05 <= ts <= t1 + 0.15] or [r for (_, r) in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_sample_inputs():
+    """Bounded sample of the config-2 workload for the host-core baseline: one of the two timesteps on a
+    quarter-area crop of the latent (135x240 -> 540x960 = 518 400 queries); per-query work and scale
+    factor are those of config 2."""
+    from oracle import synth
+    w = synth.make_weights(0, False)
+    lat, fr = synth.make_inputs(0, 1, 135, 240, 0.05)
+    return w, lat, fr, [0.5], (540, 960), "config2 quarter-area crop: 135x240 latent -> 540x960, t=[0.5], 518400 queries"
+
+
+def run_cpu_port(steps: int, warmup: int):
+    import torch
+    from oracle import port_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    w, lat, fr, times, scale, what = cpu_sample_inputs()
+    nq = scale[0] * scale[1] * len(times)
+    for _ in range(warmup):
+        port_torch.decode(lat, fr, w, times, scale)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        port_torch.decode(lat, fr, w, times, scale)
+        ts.append(time.perf_counter() - t0)
+    sec = float(np.mean(ts))
+    return {"value": nq / sec, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": what, "sec_per_step": sec, "best_sec": float(np.min(ts))}
+
+
+def main_reference(args):
+    """`--impl reference`: the reference algorithm on the box's host cores (torch CPU port of
+    LunaTokis.decoding, oracle/port_torch.py -- the reference itself is Python and does not travel)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, W, HH, WW, times = WORKLOADS[args.workload]
+    res = run_cpu_port(max(1, args.steps), max(1, min(args.warmup, 1)))
+    line = {"impl": "reference", "metric": "decoded space-time queries/sec", "value": res["value"], "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {H}x{W} latent -> {HH}x{WW}, times {times}; timed on a bounded sample",
+                       "sample": res["sample"]},
+            "cpu_baseline": {"value": res["value"], "unit": "queries/s", "cores": res["cores"], "kind": "port",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import stif_b200
+    from oracle import synth  # seeded synthetic inputs only (fixture generator, not the checker)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    H, W, HH, WW, times = WORKLOADS[args.workload]
+    T = len(times)
+    nq_rank = HH * WW * T
+
+    # weights: created on rank 0, broadcast once over NCCL (0.84 MB); latents: one frame pair per rank
+    keys = stif_b200.weight_keys()
+    shapes = synth.weight_shapes()
+    flat = torch.zeros(sum(int(np.prod(shapes[k])) for k in keys), device="cuda")
+    if rank == 0:
+        w0 = synth.make_weights(0, args.stress_weights)
+        flat.copy_(torch.from_numpy(np.concatenate([w0[k].ravel() for k in keys])))
+    t_bcast = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
+        dist.broadcast(flat, 0)
+        torch.cuda.synchronize()
+        t_bcast = time.perf_counter() - tb
+    weights, off = {}, 0
+    flat_h = flat.cpu().numpy()
+    for k in keys:
+        n = int(np.prod(shapes[k]))
+        weights[k] = flat_h[off:off + n].reshape(shapes[k]).copy()
+        off += n
+    lat_h, fr_h = synth.make_inputs(100 + rank, 1, H, W, 0.05)
+    dec = stif_b200.STIFQueryDecoder(local, mode=args.mode)
+    dec.load_weights(weights)
+    lat = torch.from_numpy(lat_h).cuda()
+    fr = torch.from_numpy(fr_h).cuda()
+    out = torch.empty((T, 1, 3, HH, WW), device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        dec.decode_stacked(lat, fr, times, (HH, WW), out=out)
+    barrier()
+    # ---- timed region 1: inputs resident in HBM (value)
+    dec.profile(True)
+    dec.profile_read()
+    l0 = dec.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = sampler.mark()
+    ev0.record()
+    for _ in range(args.steps):
+        dec.decode_stacked(lat, fr, times, (HH, WW), out=out)
+    ev1.record()
+    barrier()
+    w1 = sampler.mark()
+    ms_step = maxreduce(ev0.elapsed_time(ev1) / args.steps)
+    launches = dec.launch_count - l0
+    prof = dec.profile_read()
+    dec.profile(False)
+    # ---- timed region 2: end to end through the C-ABI host entry point (pinned host buffers, H2D + D2H inside)
+    lat_p, fr_p = torch.from_numpy(lat_h).pin_memory(), torch.from_numpy(fr_h).pin_memory()
+    out_p = torch.empty((T, 1, 3, HH, WW)).pin_memory()
+    for _ in range(2):
+        dec.decode_host(lat_p, fr_p, times, (HH, WW), out=out_p)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        dec.decode_host(lat_p, fr_p, times, (HH, WW), out=out_p)   # synchronous: returns after the D2H copy
+    e2e_sec = maxreduce((time.perf_counter() - t0) / args.steps)
+    barrier()
+    checksum = float(out_p.double().abs().mean())
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak_burst, peak_sust, peak_src = measured_peaks()
+    qps = world * nq_rank / (ms_step * 1e-3)
+    # dominant kernel group and its roofline (tensor pipe): algorithmic FLOP per launch / mean launch duration
+    groups = {"K0_project_latent": 0, "K1_stageAB_feat_flow": 1, "K2_stageCDE_warp_encode": 2}
+    per = {}
+    for name, k in groups.items():
+        if prof["count"][k]:
+            per[name] = prof["ms"][k] / prof["count"][k]
+    dom = max((n for n in per if not n.startswith("K0")), key=lambda n: per[n])
+    flop_launch = (FLOP_K1 if dom.startswith("K1") else FLOP_K2) * HH * WW
+    achieved = flop_launch / (per[dom] * 1e-3) / 1e12
+    kernel_ms = sum(prof["ms"]) / args.steps
+    roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
+            "frac": achieved / peak_burst, "peak_source": f"{peak_src} (burst; sustained {peak_sust})",
+            "traffic": None, "ms_per_launch": per[dom],
+            "all_kernels_ms_per_launch": per,
+            "share_of_step": {n: per[n] * prof["count"][groups[n]] / args.steps / kernel_ms for n in per},
+            "whole_step_frac": qps / world * FLOP_PER_QUERY / 1e12 / peak_burst}
+    line = {"metric": "decoded space-time queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: B=1 {H}x{W} latent -> {HH}x{WW}, times {times} "
+                                   f"({nq_rank} queries per rank per step); one frame pair per rank",
+                       "weights": "SIREN-init seed 0" + (" stress variant" if args.stress_weights else ""),
+                       "l2": "no flush: per-step working set (latent 100 MB + tables + 50 MB output) exceeds the 126 MB L2",
+                       "weight_broadcast_s": t_bcast, "mode": args.mode},
+            "roofline": roof,
+            "e2e": {"value": world * nq_rank / e2e_sec, "unit": "queries/s",
+                    "h2d_bytes_per_step": int(lat_p.numel() * 4 + fr_p.numel() * 4),
+                    "d2h_bytes_per_step": int(out_p.numel() * 4), "ms_per_step": e2e_sec * 1e3,
+                    "api": "stif_decode_host (C ABI) on pinned host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(w0, w1),
+            "output_checksum": checksum}
+    if world == 1 and not args.no_cpu_baseline:
+        cb = run_cpu_port(args.cpu_steps, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--stress-weights", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,161 @@
+/* stif_b200.h -- C ABI of the B200-native STIF space-time query decoder.
+ *
+ * This is the drop-in boundary for ONE path of paperwave/STIF-continuous-video-representation:
+ * `LunaTokis.decoding(times, scale)` and its siblings
+ * (reference: codes/models/modules/Sakuya_arch_test.py:364-459, :863-960, :962-1085), i.e. the
+ * three-SIREN continuous space-time decoder that turns the encoder's latent volume
+ * (`self.feat` [B,3,64,H,W], set at :361) and the LR frame pair (`self.inp` [B,2,3,H,W], :1224)
+ * into RGB at an arbitrary output raster (HH,WW) and arbitrary times t.
+ *
+ * The reference has no FFI for this path: the boundary there is a Python
+ * method on the model.  The only FFI precedent in the reference is the DCNv2 extension
+ * (codes/models/modules/DCNv2/src/vision.cpp:4-9, src/dcn_v2.h:9-39): free functions taking device
+ * buffers, asserting CUDA residency, erroring on unsupported devices, running on the
+ * caller's current stream.  This header follows that precedent with plain C types:
+ * pointers + sizes in, int status out, no torch types.  INTEGRATION.md shows the ctypes
+ * binding and the class-level patch a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative STIF_E* code on failure;
+ *     stif_last_error() returns a thread-local human-readable message for the last failure.
+ *   - "dev" pointers are CUDA device pointers on the decoder's device; "host" pointers are
+ *     ordinary host memory.  There is NO CPU fallback: without a usable sm_100 device
+ *     stif_create fails with STIF_ENODEV.
+ *   - all work is stream-ordered on the cudaStream_t passed as `void* stream`
+ *     (NULL = legacy default stream).  A handle is not re-entrant.
+ *   - the caller owns every buffer, including the workspace; the library owns only its
+ *     packed copy of the weights and a few KB of per-geometry axis tables.
+ */
+#ifndef STIF_B200_H_
+#define STIF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STIF_ABI_VERSION 1
+
+/* status codes */
+#define STIF_OK        0
+#define STIF_EINVAL   -1   /* bad argument (shape, null pointer, unknown mode ...)          */
+#define STIF_ENODEV   -2   /* no CUDA device / not an sm_100 device / kernels not loadable  */
+#define STIF_ECUDA    -3   /* a CUDA runtime call or kernel launch failed                   */
+#define STIF_ENOMEM   -4   /* workspace too small (see stif_workspace_bytes)                */
+#define STIF_ESTATE   -5   /* weights not loaded yet                                        */
+
+/* precision / algorithm modes (the `mode` argument) */
+#define STIF_MODE_BF16      0  /* tcgen05 bf16 tensor-core kernels, fp32 accumulate; RGB within 2e-2 of the reference */
+#define STIF_MODE_FP32      1  /* fp32 FMA-pipe kernels; RGB within 1e-4 of the reference                           */
+/* flags OR-ed into `mode` */
+#define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085) */
+
+/* number of weight tensors the decoder consumes (state-dict order, see stif_load_weights) */
+#define STIF_NUM_WEIGHT_TENSORS 26
+
+typedef struct stif_decoder stif_decoder_t;
+
+/* ABI version of the loaded library (compare with STIF_ABI_VERSION). */
+int stif_abi_version(void);
+
+/* Message for the most recent failure on the calling thread ("" if none). */
+const char* stif_last_error(void);
+
+/* Create a decoder bound to CUDA device `device`.
+ * Replaces: model construction + `.to('cuda')` for the decoder part
+ * (codes/custom_video_test.py:35-39). */
+int stif_create(stif_decoder_t** out, int device);
+
+int stif_destroy(stif_decoder_t* dec);
+
+/* Load the 26 decoder tensors, fp32, HOST pointers, in this order (shapes [out,in] / [out]):
+ *   feat_imnet.net.{0,1,2}.linear.{weight,bias}, feat_imnet.net.3.{weight,bias},
+ *   flow_imnet.net.{0,1,2}.linear.{weight,bias}, flow_imnet.net.3.{weight,bias},
+ *   encode_imnet.net.{0,1,2,3}.linear.{weight,bias}, encode_imnet.net.4.{weight,bias}
+ * i.e. [64,201],[64] [64,64],[64] [256,64],[256] [64,256],[64] | [64,263].. [4,256],[4] |
+ * [64,525].. [256,256],[256] [3,256],[3].
+ * Replaces: `model.load_state_dict(torch.load('latest_G.pth'), strict=True)` for the decoder
+ * sub-modules (codes/custom_video_test.py:36; layer shapes Sakuya_arch_test.py:306-311).
+ * The library folds omega_0 = 30 (SIREN.py:45) into its packed copy and synchronises the
+ * device before returning, so the host buffers may be freed immediately. */
+int stif_load_weights(stif_decoder_t* dec, const float* const* tensors_host, int num_tensors);
+
+/* Bytes of device workspace stif_decode needs for this problem (0 on invalid arguments). */
+size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode);
+
+/* Decode.  Replaces `LunaTokis.decoding(times, scale)` (Sakuya_arch_test.py:364-459).
+ *   latent_dev  [B,3,64,H,W] fp32  (== self.feat; channel c of the 192 = (c/64, c%64))
+ *   frames_dev  [B,2,3,H,W]  fp32  (== self.inp)
+ *   times_host  [T,B] fp32         (times[c][b]; the reference passes [1,1] or [B,1] tensors per c)
+ *   (HH,WW)     output raster size; the reference's `scale` argument IS this size
+ *               (Sakuya_arch_test.py:368-371); the x4 default is (4H,4W)
+ *   out_rgb_dev [T,B,3,HH,WW] fp32, unclamped (== torch.stack(preds))
+ * With STIF_FLAG_LOCAL_ENSEMBLE the result is decoding_localensemble's (B must be 1 there, as in the
+ * reference, and out is [T,3,HH,WW]). */
+int stif_decode(stif_decoder_t* dec,
+                const float* latent_dev, const float* frames_dev,
+                int B, int H, int W, int HH, int WW,
+                const float* times_host, int T, int mode,
+                void* workspace_dev, size_t workspace_bytes,
+                float* out_rgb_dev, void* stream);
+
+/* Same as stif_decode but the query raster is restricted to rows [row_begin,row_end) of every
+ * (t,b) slab -- the unit the multi-GPU launcher shards when slabs < GPUs.  Stage A/B of the
+ * reference are point-wise (Sakuya_arch_test.py:382-422), so the halo rows the warp of
+ * stage D may reach (|flow_y| pixels, :424-453) are recomputed locally: rows
+ * [row_begin-halo, row_end+halo) are decoded through stage A/B and the call FAILS with
+ * STIF_EINVAL (message names the needed halo) if a flow reaches outside that band.
+ * out_rgb_dev is still addressed as the full [T,B,3,HH,WW] tensor; only the band is written. */
+int stif_decode_rows(stif_decoder_t* dec,
+                     const float* latent_dev, const float* frames_dev,
+                     int B, int H, int W, int HH, int WW,
+                     const float* times_host, int T, int mode,
+                     int row_begin, int row_end, int halo,
+                     void* workspace_dev, size_t workspace_bytes,
+                     float* out_rgb_dev, void* stream);
+
+/* End-to-end convenience for FFI callers that hold HOST buffers: allocates device memory
+ * internally (cached on the handle), copies latent/frames host->device, decodes, copies RGB
+ * device->host, synchronises.  This is the call bench.py's `e2e` number goes through. */
+int stif_decode_host(stif_decoder_t* dec,
+                     const float* latent_host, const float* frames_host,
+                     int B, int H, int W, int HH, int WW,
+                     const float* times_host, int T, int mode,
+                     float* out_rgb_host);
+
+/* ---- introspection used by the parity tests (same device functions as the decode path) ---- */
+
+/* Per-axis query tables for an (n_lr -> n_hr) axis, HOST outputs of length n_hr (any may be NULL):
+ *   coord  clamped pixel-centre query coordinate   (make_coord :1233-1248 + clamp :373)
+ *   index  nearest LR texel (grid_sample nearest, :382-393)            -- bit-exact contract
+ *   rel    (coord - lr_coord[index]) * n_lr         (:394-396)         -- bit-exact contract
+ *   base   warp base grid, linspace(-1,1,n_hr)      (warplayer.py:28-31) */
+int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* rel, float* base);
+
+/* Copy stage intermediates of the LAST slab decoded by `dec` to HOST buffers (any may be NULL):
+ *   flow [HH*WW,4] fp32 -- flow_imnet output (dx1,dy1,dx2,dy2), HR-pixel units (:419-422).
+ * Returns STIF_ESTATE if no decode has run. */
+int stif_debug_last_flow(stif_decoder_t* dec, float* flow_host, size_t num_floats);
+
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int64_t stif_launch_count(const stif_decoder_t* dec);
+
+/* Per-kernel device timing.  While enabled, stif_decode brackets each kernel group with CUDA
+ * events on the caller's stream: group 0 = latent projection (K0), 1 = stage A+B (K1),
+ * 2 = stage C+D+E (K2).  stif_profile_read synchronises the device, adds the elapsed
+ * milliseconds and group launch counts accumulated since the last read into ms[3] / count[3]
+ * (overwriting them) and resets the accumulators.  bench.py's roofline uses this. */
+int stif_profile_enable(stif_decoder_t* dec, int enable);
+int stif_profile_read(stif_decoder_t* dec, double* ms, int64_t* count);
+
+/* Run the built-in tcgen05/TMEM unit checks on the device (small GEMMs against a host fp32
+ * reference).  Writes a report into `report` (NUL-terminated, truncated to cap).  Returns 0 if
+ * every check passed. */
+int stif_selftest(int device, char* report, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STIF_B200_H_ */

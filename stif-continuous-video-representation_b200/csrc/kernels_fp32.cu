@@ -1,0 +1,247 @@
+// kernels_fp32.cu -- fp32 FMA-pipe path of the STIF query decoder (STIF_MODE_FP32) and the
+// latent-projection kernel shared with the bf16 path.
+//
+// This is the high-precision mode (RGB within 1e-4 of the reference): the hoisted formulation of
+// DESIGN.md section 3 evaluated layer by layer in fp32 with accurate sinf.  Activations round-trip
+// through the caller's workspace in query chunks; it is the parity anchor for the fused tcgen05
+// kernels, not the throughput path.
+//
+// Reference semantics: LunaTokis.decoding, codes/models/modules/Sakuya_arch_test.py:364-459.
+#include <cstdio>
+
+#include "stif_internal.h"
+
+namespace stif {
+namespace {
+
+struct GemmArgs {
+  const float* A;    // A(m,k) = A[m*sam + k*sak]               for k <  ksplit
+  const float* A2;   // A(m,k) = A2[m*sam + (k-ksplit)*sak]     for k >= ksplit (may be null)
+  long sam, sak;
+  int ksplit;
+  const float* Wt;   // [N,K] row-major
+  const float* bias; // [N] or null
+  void* C;           // C(m,n) at C[m*scm + n*scn]
+  long scm, scn;
+  long M;
+  int N, K;
+  int act;           // 0 = identity, 1 = sin
+  int out_half;      // store __half instead of float
+};
+
+constexpr int BM = 128, BN = 64, BK = 16;
+
+// C = act(A W^T + b).  256 threads, 128x64 tile, each thread 8 rows x 4 cols.
+template <bool A_MCONTIG>
+__global__ void __launch_bounds__(256) sgemm_bias_act_kernel(GemmArgs g) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long m0 = (long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int idx = tid + i * 256, m, k;
+      if (A_MCONTIG) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
+      long gm = m0 + m;
+      int gk = k0 + k;
+      float v = 0.f;
+      if (gm < g.M && gk < g.K)
+        v = (gk < g.ksplit) ? g.A[gm * g.sam + (long)gk * g.sak] : g.A2[gm * g.sam + (long)(gk - g.ksplit) * g.sak];
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int idx = tid + i * 256, k = idx % BK, n = idx / BK;
+      int gn = n0 + n, gk = k0 + k;
+      Ws[k][n] = (gn < g.N && gk < g.K) ? g.Wt[(long)gn * g.K + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], w[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long gm = m0 + ty * 8 + i;
+    if (gm >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= g.N) continue;
+      float v = acc[i][j] + (g.bias ? g.bias[gn] : 0.f);
+      if (g.act == 1) v = sinf(v);
+      long o = gm * g.scm + (long)gn * g.scn;
+      if (g.out_half) reinterpret_cast<__half*>(g.C)[o] = __float2half_rn(v);
+      else reinterpret_cast<float*>(g.C)[o] = v;
+    }
+  }
+}
+
+cudaError_t launch_gemm(const LaunchCtx& cx, const GemmArgs& g, bool a_mcontig) {
+  if (g.M <= 0) return cudaSuccess;
+  dim3 grid((unsigned)((g.M + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN));
+  if (a_mcontig) sgemm_bias_act_kernel<true><<<grid, 256, 0, cx.stream>>>(g);
+  else sgemm_bias_act_kernel<false><<<grid, 256, 0, cx.stream>>>(g);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
+GemmArgs dense(const float* A, int K, const float* Wt, const float* bias, void* C, long ldc, long M, int N, int act) {
+  GemmArgs g{};
+  g.A = A; g.A2 = nullptr; g.sam = K; g.sak = 1; g.ksplit = K;
+  g.Wt = Wt; g.bias = bias; g.C = C; g.scm = ldc; g.scn = 1; g.M = M; g.N = N; g.K = K; g.act = act; g.out_half = 0;
+  return g;
+}
+
+struct Vec64 { float v[64]; };
+
+// Stage A first layer (hoisted): h0 = sin(TA[iy,ix] + rel_y*w_ry + rel_x*w_rx + (w_t t + b))
+// reference: Sakuya_arch_test.py:382-400 (nearest gathers, rel_coord, pe_coord, first SineLayer).
+__global__ void stage_a_first_layer(const float* __restrict__ tab, Geometry g, const float* __restrict__ a_rel, Vec64 cst,
+                                    long q0, long n, float* __restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 64) return;
+  int c = (int)(i & 63);
+  long q = q0 + (i >> 6);
+  int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  int iy = g.y.idx[jy], ix = g.x.idx[jx];
+  float ta = 0.f;
+  if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) ta = tab[((long)iy * g.W + ix) * 256 + c];
+  float v = ta + g.y.rel[jy] * a_rel[c * 2 + 0] + g.x.rel[jx] * a_rel[c * 2 + 1] + cst.v[c];
+  out[i] = sinf(v);
+}
+
+// Stage B first layer (hoisted): f0 = sin(F + bilinear(TB; query position) + (w_t t + b))
+// reference: Sakuya_arch_test.py:406-419.
+__global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, Vec64 cst, long q0, long n,
+                                    float* __restrict__ f_inout) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 64) return;
+  int c = (int)(i & 63);
+  long q = q0 + (i >> 6);
+  int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  Taps tp = make_taps_tables(g, jy, jx);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s = fmaf(tp.w[k], tab[(long)tp.off[k] * 256 + 64 + c], s);
+  f_inout[i] = sinf(f_inout[i] + s + cst.v[c]);
+}
+
+// Stage C+D + encode_imnet first layer (hoisted):
+// e0 = sin(bilin(Q1;g1) + bilin(Q2;g2) + bilin(TE1;g1) + bilin(TE2;g2) + (w_t t + b))
+// reference: warplayer.py:25-39, Sakuya_arch_test.py:424-456.
+__global__ void stage_e_first_layer(const float* __restrict__ tab, const float* __restrict__ qtab,
+                                    const float* __restrict__ flow, Geometry g, Vec64 cst, long q0, long n,
+                                    int band_lo, int band_hi, int* __restrict__ flag, float* __restrict__ out) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 64) return;
+  int c = (int)(i & 63);
+  long q = q0 + (i >> 6);
+  int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  float4 fl = reinterpret_cast<const float4*>(flow)[q];
+  float s = cst.v[c];
+#pragma unroll
+  for (int wv = 0; wv < 2; ++wv) {
+    float gy, gx;
+    warp_position(g, jy, jx, wv == 0 ? fl.x : fl.z, wv == 0 ? fl.y : fl.w, gy, gx);
+    Taps hr = make_taps(gy, gx, g.HH, g.WW);
+    Taps lr = make_taps(gy, gx, g.H, g.W);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (hr.w[k] != 0.f) {
+        int row = hr.off[k] / g.WW;
+        if (row < band_lo || row >= band_hi) { if (c == 0) atomicOr(flag, 1); continue; }
+      }
+      s = fmaf(hr.w[k], qtab[(long)hr.off[k] * 128 + wv * 64 + c], s);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fmaf(lr.w[k], tab[(long)lr.off[k] * 256 + 128 + wv * 64 + c], s);
+  }
+  out[i] = sinf(s);
+}
+
+Vec64 time_constant(const std::vector<float>& wt, const std::vector<float>& b, float t) {
+  Vec64 v;
+  for (int c = 0; c < 64; ++c) v.v[c] = wt[c] * t + b[c];
+  return v;
+}
+
+}  // namespace
+
+// tab[texel, 0:256] = w_tab [256,198] . [latent(192); frames(6)][texel]      (t-independent)
+cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
+                           int H, int W, void* tab, bool tab_half) {
+  GemmArgs g{};
+  g.A = latent192; g.A2 = frames6; g.sam = 1; g.sak = (long)H * W; g.ksplit = 192;
+  g.Wt = w.w_tab; g.bias = nullptr; g.C = tab; g.scm = 256; g.scn = 1;
+  g.M = (long)H * W; g.N = 256; g.K = 198; g.act = 0; g.out_half = tab_half ? 1 : 0;
+  return launch_gemm(cx, g, true);
+}
+
+#define STIF_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
+
+cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
+                             const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
+                             int k1_row_end, float* out_rgb, int stage) {
+  const long WW = geo.WW;
+  const long Qall = (long)geo.HH * geo.WW;
+  const float* tab = reinterpret_cast<const float*>(ws.tab);
+  float* qtab = reinterpret_cast<float*>(ws.qtab);
+  const Vec64 cA = time_constant(hw.a_t, hw.a_b, t), cB = time_constant(hw.b_t, hw.b_b, t),
+              cE = time_constant(hw.e_t, hw.e_b, t);
+  const long chunk = (long)ws.chunk;
+  // ---- K1: stage A + B over rows [k1_row_begin, k1_row_end)
+  for (long q0 = k1_row_begin * WW; stage == 1 && q0 < k1_row_end * WW; q0 += chunk) {
+    long n = std::min(chunk, k1_row_end * WW - q0);
+    unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+    stage_a_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, w.a_rel, cA, q0, n, ws.act_c);
+    ++*cx.launch_counter;
+    STIF_TRY(cudaGetLastError());
+    STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 64, 1), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 64, 0), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
+    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c);
+    ++*cx.launch_counter;
+    STIF_TRY(cudaGetLastError());
+    STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 256, 1), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, n, 4, 0), false));
+  }
+  // ---- K2: stage C + D + E over rows [row_begin, row_end)
+  for (long q0 = row_begin * WW; stage == 2 && q0 < row_end * WW; q0 += chunk) {
+    long n = std::min(chunk, row_end * WW - q0);
+    unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+    stage_e_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end,
+                                                      ws.flag, ws.act_c);
+    ++*cx.launch_counter;
+    STIF_TRY(cudaGetLastError());
+    STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 64, 1), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.e2_w, w.e2_b, ws.act_b, 256, n, 256, 1), false));
+    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.e3_w, w.e3_b, ws.act_a, 256, n, 256, 1), false));
+    GemmArgs g = dense(ws.act_a, 256, w.e4_w, w.e4_b, out_rgb + q0, 1, n, 3, 0);
+    g.scm = 1; g.scn = Qall;  // planar [3,HH,WW] (Sakuya_arch_test.py:457)
+    STIF_TRY(launch_gemm(cx, g, false));
+  }
+  return cudaSuccess;
+}
+
+}  // namespace stif

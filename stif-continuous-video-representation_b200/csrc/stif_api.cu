@@ -1,0 +1,415 @@
+// stif_api.cu -- the C ABI of libstif_b200.so (include/stif_b200.h): handle, weight upload,
+// geometry cache, workspace carve-up and the per-slab orchestration of the decode kernels.
+//
+// Orchestration mirrors LunaTokis.decoding (codes/models/modules/Sakuya_arch_test.py:364-459):
+//   for each batch item b:   project the latent once (t-independent work the reference repeats per t)
+//     for each time c:       K1 = stage A+B (feat_imnet, flow_imnet), K2 = stage C+D+E (warp, encode_imnet)
+#include <algorithm>
+#include <array>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+
+#include "../../include/stif_b200.h"
+#include "stif_internal.h"
+
+using namespace stif;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_OR_RETURN(expr)                                                                        \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) return set_error(STIF_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+struct DeviceGeometry {
+  Geometry geo{};
+  void* blob = nullptr;  // one allocation holding all axis tables
+};
+
+}  // namespace
+
+struct stif_decoder {
+  int device = 0;
+  int num_sms = 0;
+  bool weights_loaded = false;
+  FoldedWeights hw;
+  float* d_w32 = nullptr;  // fp32 folded weights (one allocation)
+  DeviceWeights32 w32{};
+  TcWeights* tcw = nullptr;
+  std::map<std::array<int, 4>, DeviceGeometry> geos;
+  int64_t launches = 0;
+  // last decoded slab (debug introspection)
+  const float* last_flow = nullptr;
+  size_t last_flow_floats = 0;
+  // per-kernel-group event timing (stif_profile_*)
+  bool profiling = false;
+  struct Span { cudaEvent_t a, b; int kind; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  // stif_decode_host scratch
+  void* host_scratch = nullptr;
+  size_t host_scratch_bytes = 0;
+  cudaStream_t host_stream = nullptr;
+};
+
+namespace stif {
+
+Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
+  Workspace ws{};
+  const bool fp32 = (mode & 0xFF) == STIF_MODE_FP32;
+  const size_t esz = fp32 ? 4 : 2;
+  const size_t Q = (size_t)HH * WW;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((char*)base + off) : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  ws.tab = take((size_t)H * W * 256 * esz);
+  ws.qtab = take(Q * 128 * esz);
+  ws.flow = (float*)take(Q * 4 * sizeof(float));
+  ws.flag = (int*)take(256);
+  if (fp32) {
+    ws.chunk = std::min<size_t>(Q, (size_t)1 << 18);
+    ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
+    ws.act_b = (float*)take(ws.chunk * 256 * sizeof(float));
+    ws.act_c = (float*)take(ws.chunk * 64 * sizeof(float));
+  } else {
+    ws.chunk = Q;
+  }
+  ws.total_bytes = off;
+  return ws;
+}
+
+}  // namespace stif
+
+namespace {
+
+int check_shape(int B, int H, int W, int HH, int WW, int T) {
+  if (B < 1 || H < 1 || W < 1 || HH < 1 || WW < 1 || T < 1)
+    return set_error(STIF_EINVAL, "invalid shape B=%d H=%d W=%d HH=%d WW=%d T=%d", B, H, W, HH, WW, T);
+  if ((long long)HH * WW > (1ll << 30) || (long long)H * W > (1ll << 28))
+    return set_error(STIF_EINVAL, "raster too large (HH*WW=%lld, H*W=%lld)", (long long)HH * WW, (long long)H * W);
+  return STIF_OK;
+}
+
+int get_geometry(stif_decoder* d, int H, int W, int HH, int WW, cudaStream_t stream, const Geometry** out) {
+  std::array<int, 4> key{H, W, HH, WW};
+  auto it = d->geos.find(key);
+  if (it == d->geos.end()) {
+    HostAxis ay, ax;
+    build_axis(H, HH, ay);
+    build_axis(W, WW, ax);
+    // blob layout: y{idx,rel,b0,bw,base} x{idx,rel,b0,bw,base}, each 256-byte aligned
+    size_t ny = align256((size_t)HH * 4), nx = align256((size_t)WW * 4);
+    size_t total = 5 * ny + 5 * nx;
+    std::vector<char> host(total, 0);
+    auto put = [&](size_t off, const void* src, size_t n) { memcpy(host.data() + off, src, n); };
+    put(0 * ny, ay.idx.data(), HH * 4); put(1 * ny, ay.rel.data(), HH * 4); put(2 * ny, ay.b0.data(), HH * 4);
+    put(3 * ny, ay.bw.data(), HH * 4);  put(4 * ny, ay.base.data(), HH * 4);
+    size_t xo = 5 * ny;
+    put(xo + 0 * nx, ax.idx.data(), WW * 4); put(xo + 1 * nx, ax.rel.data(), WW * 4); put(xo + 2 * nx, ax.b0.data(), WW * 4);
+    put(xo + 3 * nx, ax.bw.data(), WW * 4);  put(xo + 4 * nx, ax.base.data(), WW * 4);
+    DeviceGeometry dg;
+    CUDA_OR_RETURN(cudaMalloc(&dg.blob, total));
+    // synchronous copy: `host` dies at scope exit
+    CUDA_OR_RETURN(cudaMemcpy(dg.blob, host.data(), total, cudaMemcpyHostToDevice));
+    char* b = (char*)dg.blob;
+    Geometry& g = dg.geo;
+    g.H = H; g.W = W; g.HH = HH; g.WW = WW;
+    g.y = AxisTables{(const int32_t*)(b + 0 * ny), (const float*)(b + 1 * ny), (const int32_t*)(b + 2 * ny),
+                     (const float*)(b + 3 * ny), (const float*)(b + 4 * ny)};
+    g.x = AxisTables{(const int32_t*)(b + xo + 0 * nx), (const float*)(b + xo + 1 * nx), (const int32_t*)(b + xo + 2 * nx),
+                     (const float*)(b + xo + 3 * nx), (const float*)(b + xo + 4 * nx)};
+    g.half_h = (float)((HH - 1.0) / 2.0);  // python double -> fp32 at the tensor division (warplayer.py:35-36)
+    g.half_w = (float)((WW - 1.0) / 2.0);
+    if (d->geos.size() > 64) {  // bounded cache (the reference's warp-grid cache is unbounded, warplayer.py:6)
+      for (auto& kv : d->geos) cudaFree(kv.second.blob);
+      d->geos.clear();
+    }
+    it = d->geos.emplace(key, dg).first;
+  }
+  *out = &it->second.geo;
+  (void)stream;
+  return STIF_OK;
+}
+
+cudaEvent_t take_event(stif_decoder* d) {
+  if (!d->event_pool.empty()) { cudaEvent_t e = d->event_pool.back(); d->event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ScopedSpan {  // brackets one kernel group with events when profiling is on
+  stif_decoder* d; cudaStream_t s; cudaEvent_t b = nullptr;
+  ScopedSpan(stif_decoder* d_, cudaStream_t s_, int kind) : d(d_), s(s_) {
+    if (!d->profiling) return;
+    cudaEvent_t a = take_event(d);
+    b = take_event(d);
+    cudaEventRecord(a, s);
+    d->spans.push_back({a, b, kind});
+  }
+  ~ScopedSpan() { if (b) cudaEventRecord(b, s); }
+};
+
+int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
+                const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
+                size_t workspace_bytes, float* out, cudaStream_t stream, bool check_band) {
+  if (!d) return set_error(STIF_EINVAL, "null decoder");
+  if (!d->weights_loaded) return set_error(STIF_ESTATE, "stif_load_weights has not been called");
+  if (!latent || !frames || !times || !out || !workspace) return set_error(STIF_EINVAL, "null buffer");
+  if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
+  const int prec = mode & 0xFF;
+  if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
+  if (mode & STIF_FLAG_LOCAL_ENSEMBLE)
+    return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE is not implemented in this build");
+  if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
+    return set_error(STIF_EINVAL, "invalid row band [%d,%d) halo %d for HH=%d", row_begin, row_end, halo, HH);
+  const size_t need = stif_workspace_bytes(B, H, W, HH, WW, T, mode);
+  if (workspace_bytes < need)
+    return set_error(STIF_ENOMEM, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
+  CUDA_OR_RETURN(cudaSetDevice(d->device));
+  const Geometry* geo = nullptr;
+  if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo)) return rc;
+  Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
+  LaunchCtx cx{stream, &d->launches, d->num_sms};
+  const int k1_lo = std::max(0, row_begin - halo), k1_hi = std::min(HH, row_end + halo);
+  const size_t Q = (size_t)HH * WW;
+  CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
+  for (int b = 0; b < B; ++b) {
+    const float* lat_b = latent + (size_t)b * 192 * H * W;
+    const float* fr_b = frames + (size_t)b * 6 * H * W;
+    {
+      ScopedSpan sp(d, stream, 0);
+      CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, prec == STIF_MODE_BF16));
+    }
+    for (int c = 0; c < T; ++c) {
+      const float t = times[(size_t)c * B + b];
+      float* out_slab = out + ((size_t)c * B + b) * 3 * Q;
+      for (int stage = 1; stage <= 2; ++stage) {
+        ScopedSpan sp(d, stream, stage);
+        cudaError_t e = (prec == STIF_MODE_FP32)
+                            ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
+                            : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage);
+        if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+      }
+    }
+  }
+  d->last_flow = ws.flow;
+  d->last_flow_floats = Q * 4;
+  if (check_band) {
+    int flag = 0;
+    CUDA_OR_RETURN(cudaMemcpyAsync(&flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_OR_RETURN(cudaStreamSynchronize(stream));
+    if (flag)
+      return set_error(STIF_EINVAL, "row band [%d,%d): a warp reached outside the %d-row halo; increase halo", row_begin,
+                       row_end, halo);
+  }
+  return STIF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int stif_abi_version(void) { return STIF_ABI_VERSION; }
+
+const char* stif_last_error(void) { return g_last_error.c_str(); }
+
+int stif_create(stif_decoder_t** out, int device) {
+  if (!out) return set_error(STIF_EINVAL, "null out pointer");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return set_error(STIF_ENODEV, "no CUDA device available (%s); this library has no CPU fallback",
+                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return set_error(STIF_ENODEV, "device %d out of range (count %d)", device, n);
+  cudaDeviceProp prop;
+  CUDA_OR_RETURN(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(STIF_ENODEV, "device %d is sm_%d%d; libstif_b200 is built for sm_100a only", device, prop.major,
+                     prop.minor);
+  CUDA_OR_RETURN(cudaSetDevice(device));
+  auto* d = new stif_decoder();
+  d->device = device;
+  d->num_sms = prop.multiProcessorCount;
+  *out = d;
+  return STIF_OK;
+}
+
+int stif_destroy(stif_decoder_t* d) {
+  if (!d) return STIF_OK;
+  cudaSetDevice(d->device);
+  for (auto& kv : d->geos) cudaFree(kv.second.blob);
+  if (d->d_w32) cudaFree(d->d_w32);
+  if (d->tcw) tc_weights_destroy(d->tcw);
+  if (d->host_scratch) cudaFree(d->host_scratch);
+  if (d->host_stream) cudaStreamDestroy(d->host_stream);
+  for (auto& sp : d->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : d->event_pool) cudaEventDestroy(e);
+  delete d;
+  return STIF_OK;
+}
+
+int stif_load_weights(stif_decoder_t* d, const float* const* tensors, int num_tensors) {
+  if (!d || !tensors) return set_error(STIF_EINVAL, "null argument");
+  if (num_tensors != STIF_NUM_WEIGHT_TENSORS)
+    return set_error(STIF_EINVAL, "expected %d weight tensors, got %d", STIF_NUM_WEIGHT_TENSORS, num_tensors);
+  for (int i = 0; i < num_tensors; ++i)
+    if (!tensors[i]) return set_error(STIF_EINVAL, "weight tensor %d is null", i);
+  CUDA_OR_RETURN(cudaSetDevice(d->device));
+  fold_weights(tensors, d->hw);
+  const FoldedWeights& h = d->hw;
+  const std::vector<float>* parts[] = {&h.w_tab, &h.a_rel, &h.a_t, &h.a_b, &h.f1_w, &h.f1_b, &h.f2_w, &h.f2_b, &h.f3_w, &h.f3_b,
+                                       &h.b_t, &h.b_b, &h.l1_w, &h.l1_b, &h.l2_w, &h.l2_b, &h.l3_w, &h.l3_b,
+                                       &h.e_t, &h.e_b, &h.e1_w, &h.e1_b, &h.e2_w, &h.e2_b, &h.e3_w, &h.e3_b, &h.e4_w, &h.e4_b};
+  constexpr int NP = sizeof(parts) / sizeof(parts[0]);
+  size_t offs[NP], total = 0;
+  for (int i = 0; i < NP; ++i) { offs[i] = total; total += (parts[i]->size() + 63) & ~size_t(63); }
+  std::vector<float> host(total, 0.f);
+  for (int i = 0; i < NP; ++i) memcpy(host.data() + offs[i], parts[i]->data(), parts[i]->size() * sizeof(float));
+  if (d->d_w32) { cudaFree(d->d_w32); d->d_w32 = nullptr; }
+  CUDA_OR_RETURN(cudaMalloc(&d->d_w32, total * sizeof(float)));
+  CUDA_OR_RETURN(cudaMemcpy(d->d_w32, host.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  const float** fields[] = {&d->w32.w_tab, &d->w32.a_rel, &d->w32.a_t, &d->w32.a_b, &d->w32.f1_w, &d->w32.f1_b, &d->w32.f2_w,
+                            &d->w32.f2_b, &d->w32.f3_w, &d->w32.f3_b, &d->w32.b_t, &d->w32.b_b, &d->w32.l1_w, &d->w32.l1_b,
+                            &d->w32.l2_w, &d->w32.l2_b, &d->w32.l3_w, &d->w32.l3_b, &d->w32.e_t, &d->w32.e_b, &d->w32.e1_w,
+                            &d->w32.e1_b, &d->w32.e2_w, &d->w32.e2_b, &d->w32.e3_w, &d->w32.e3_b, &d->w32.e4_w, &d->w32.e4_b};
+  for (int i = 0; i < NP; ++i) *fields[i] = d->d_w32 + offs[i];
+  if (d->tcw) { tc_weights_destroy(d->tcw); d->tcw = nullptr; }
+  std::string err;
+  d->tcw = tc_weights_create(d->hw, err);
+  if (!d->tcw) return set_error(STIF_ECUDA, "packing tensor-core weights failed: %s", err.c_str());
+  CUDA_OR_RETURN(cudaDeviceSynchronize());
+  d->weights_loaded = true;
+  return STIF_OK;
+}
+
+size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode) {
+  if (B < 1 || H < 1 || W < 1 || HH < 1 || WW < 1 || T < 1) return 0;
+  return carve_workspace(nullptr, H, W, HH, WW, mode).total_bytes;
+}
+
+int stif_decode(stif_decoder_t* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
+                const float* times, int T, int mode, void* workspace, size_t workspace_bytes, float* out, void* stream) {
+  return decode_impl(d, latent, frames, B, H, W, HH, WW, times, T, mode, 0, HH, 0, workspace, workspace_bytes, out,
+                     (cudaStream_t)stream, false);
+}
+
+int stif_decode_rows(stif_decoder_t* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
+                     const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
+                     size_t workspace_bytes, float* out, void* stream) {
+  return decode_impl(d, latent, frames, B, H, W, HH, WW, times, T, mode, row_begin, row_end, halo, workspace, workspace_bytes,
+                     out, (cudaStream_t)stream, true);
+}
+
+int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* frames_host, int B, int H, int W, int HH,
+                     int WW, const float* times, int T, int mode, float* out_host) {
+  if (!d) return set_error(STIF_EINVAL, "null decoder");
+  if (!latent_host || !frames_host || !out_host) return set_error(STIF_EINVAL, "null buffer");
+  if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
+  CUDA_OR_RETURN(cudaSetDevice(d->device));
+  if (!d->host_stream) CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->host_stream, cudaStreamNonBlocking));
+  const size_t lat_b = align256((size_t)B * 192 * H * W * 4), fr_b = align256((size_t)B * 6 * H * W * 4);
+  const size_t out_b = align256((size_t)T * B * 3 * HH * WW * 4);
+  const size_t ws_b = stif_workspace_bytes(B, H, W, HH, WW, T, mode);
+  const size_t total = lat_b + fr_b + out_b + ws_b;
+  if (d->host_scratch_bytes < total) {
+    if (d->host_scratch) cudaFree(d->host_scratch);
+    d->host_scratch = nullptr;
+    d->host_scratch_bytes = 0;
+    CUDA_OR_RETURN(cudaMalloc(&d->host_scratch, total));
+    d->host_scratch_bytes = total;
+  }
+  char* base = (char*)d->host_scratch;
+  float* lat = (float*)base;
+  float* fr = (float*)(base + lat_b);
+  float* out = (float*)(base + lat_b + fr_b);
+  void* ws = base + lat_b + fr_b + out_b;
+  cudaStream_t s = d->host_stream;
+  CUDA_OR_RETURN(cudaMemcpyAsync(lat, latent_host, (size_t)B * 192 * H * W * 4, cudaMemcpyHostToDevice, s));
+  CUDA_OR_RETURN(cudaMemcpyAsync(fr, frames_host, (size_t)B * 6 * H * W * 4, cudaMemcpyHostToDevice, s));
+  if (int rc = decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false)) return rc;
+  CUDA_OR_RETURN(cudaMemcpyAsync(out_host, out, (size_t)T * B * 3 * HH * WW * 4, cudaMemcpyDeviceToHost, s));
+  CUDA_OR_RETURN(cudaStreamSynchronize(s));
+  return STIF_OK;
+}
+
+int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* rel, float* base) {
+  if (n_lr < 1 || n_hr < 1) return set_error(STIF_EINVAL, "invalid axis sizes %d -> %d", n_lr, n_hr);
+  HostAxis a;
+  build_axis(n_lr, n_hr, a);
+  if (coord) memcpy(coord, a.coord.data(), (size_t)n_hr * 4);
+  if (index) memcpy(index, a.idx.data(), (size_t)n_hr * 4);
+  if (rel) memcpy(rel, a.rel.data(), (size_t)n_hr * 4);
+  if (base) memcpy(base, a.base.data(), (size_t)n_hr * 4);
+  return STIF_OK;
+}
+
+int stif_debug_last_flow(stif_decoder_t* d, float* flow_host, size_t num_floats) {
+  if (!d || !flow_host) return set_error(STIF_EINVAL, "null argument");
+  if (!d->last_flow) return set_error(STIF_ESTATE, "no decode has run on this handle");
+  if (num_floats < d->last_flow_floats)
+    return set_error(STIF_EINVAL, "flow buffer too small: %zu floats given, %zu needed", num_floats, d->last_flow_floats);
+  CUDA_OR_RETURN(cudaSetDevice(d->device));
+  CUDA_OR_RETURN(cudaDeviceSynchronize());
+  CUDA_OR_RETURN(cudaMemcpy(flow_host, d->last_flow, d->last_flow_floats * 4, cudaMemcpyDeviceToHost));
+  return STIF_OK;
+}
+
+int64_t stif_launch_count(const stif_decoder_t* d) { return d ? d->launches : 0; }
+
+int stif_profile_enable(stif_decoder_t* d, int enable) {
+  if (!d) return set_error(STIF_EINVAL, "null decoder");
+  d->profiling = enable != 0;
+  return STIF_OK;
+}
+
+int stif_profile_read(stif_decoder_t* d, double* ms, int64_t* count) {
+  if (!d || !ms || !count) return set_error(STIF_EINVAL, "null argument");
+  CUDA_OR_RETURN(cudaSetDevice(d->device));
+  CUDA_OR_RETURN(cudaDeviceSynchronize());
+  for (int k = 0; k < 3; ++k) { ms[k] = 0.0; count[k] = 0; }
+  for (auto& sp : d->spans) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ms[sp.kind] += t; count[sp.kind] += 1; }
+    d->event_pool.push_back(sp.a);
+    d->event_pool.push_back(sp.b);
+  }
+  d->spans.clear();
+  return STIF_OK;
+}
+
+int stif_selftest(int device, char* report, size_t cap) {
+  std::string rep;
+  int rc = tc_selftest(device, rep);
+  if (report && cap) {
+    size_t n = std::min(cap - 1, rep.size());
+    memcpy(report, rep.data(), n);
+    report[n] = 0;
+  }
+  if (rc != 0) set_error(STIF_ECUDA, "tcgen05 selftest failed");
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// stif_internal.h -- host-side structures shared by the translation units of libstif_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "stif_common.cuh"
+
+namespace stif {
+
+// ---------------------------------------------------------------------------------------------
+// Folded weights (pack_weights.cpp).  omega_0 = 30 is folded into every sine layer
+// (sin(30(Wx+b)) = sin((30W)x + 30b), reference SIREN.py:45) and the three consumers of HRfeat
+// are composed with feat_imnet's last linear layer.  All fp32, row-major [out,in].
+struct FoldedWeights {
+  std::vector<float> w_tab;          // [256,198]  rows: TA | TB | TE1 | TE2 ; cols: latent(192), frames(6)
+  std::vector<float> a_rel;          // [64,2]     (rely, relx) columns of feat_imnet layer 0
+  std::vector<float> a_t, a_b;       // [64]       t column / bias of feat_imnet layer 0
+  std::vector<float> f1_w, f1_b;     // [64,64]
+  std::vector<float> f2_w, f2_b;     // [256,64]
+  std::vector<float> f3_w, f3_b;     // [192,256]  rows: F | Q1 | Q2   (composed)
+  std::vector<float> b_t, b_b;       // [64]       flow_imnet layer 0
+  std::vector<float> l1_w, l1_b;     // [64,64]
+  std::vector<float> l2_w, l2_b;     // [256,64]
+  std::vector<float> l3_w, l3_b;     // [4,256]    plain linear (not scaled)
+  std::vector<float> e_t, e_b;       // [64]       encode_imnet layer 0
+  std::vector<float> e1_w, e1_b;     // [64,64]
+  std::vector<float> e2_w, e2_b;     // [256,64]
+  std::vector<float> e3_w, e3_b;     // [256,256]
+  std::vector<float> e4_w, e4_b;     // [3,256]    plain linear
+};
+
+// tensors: the 26 host pointers of stif_load_weights, in ABI order.
+void fold_weights(const float* const* tensors, FoldedWeights& out);
+
+// Device-side view of the fp32 copy (kernels_fp32.cu).
+struct DeviceWeights32 {
+  const float *w_tab, *a_rel, *a_t, *a_b, *f1_w, *f1_b, *f2_w, *f2_b, *f3_w, *f3_b;
+  const float *b_t, *b_b, *l1_w, *l1_b, *l2_w, *l2_b, *l3_w, *l3_b;
+  const float *e_t, *e_b, *e1_w, *e1_b, *e2_w, *e2_b, *e3_w, *e3_b, *e4_w, *e4_b;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Axis tables (axis_tables.cpp), host side.
+struct HostAxis {
+  std::vector<float> coord, rel, bw, base;
+  std::vector<int32_t> idx, b0;
+};
+void build_axis(int n_lr, int n_hr, HostAxis& out);
+
+// ---------------------------------------------------------------------------------------------
+// Launch plumbing shared by the kernel translation units.
+struct LaunchCtx {
+  cudaStream_t stream;
+  int64_t* launch_counter;   // incremented per kernel launch
+  int num_sms;
+};
+
+// Workspace carve-up for one decode call (all offsets 256-byte aligned).
+struct Workspace {
+  void* tab;      // [H*W,256]  fp32 (FP32 mode) or fp16 (BF16 mode)
+  void* qtab;     // [HH*WW,128] same element type as tab
+  float* flow;    // [HH*WW,4]
+  float* act_a;   // FP32 mode only: ping-pong activation buffers [chunk,256]
+  float* act_b;
+  float* act_c;   // [chunk,64]
+  int* flag;      // device int: row-band halo violation flag
+  size_t chunk;   // queries per activation chunk (FP32 mode)
+  size_t total_bytes;
+};
+Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode);
+
+// fp32 FMA-pipe path (kernels_fp32.cu)
+cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
+                           int H, int W, void* tab, bool tab_half);
+cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
+                             const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
+                             int k1_row_end, float* out_rgb /* [3,HH,WW] */, int stage /* 1 = K1 (A+B), 2 = K2 (C+D+E) */);
+
+// bf16 tcgen05 path (kernels_tc.cu)
+struct TcWeights;  // opaque: device smem images + host constant blocks
+TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err);
+void tc_weights_destroy(TcWeights*);
+cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
+                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage);
+int tc_selftest(int device, std::string& report);
+
+}  // namespace stif

@@ -1,0 +1,91 @@
+"""ctypes binding of ``libstif_b200.so`` (the C ABI declared in ``include/stif_b200.h``).
+
+There is deliberately no fallback: if the shared library has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'``) importing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libstif_b200.so"))
+
+STIF_OK = 0
+STIF_MODE_BF16 = 0
+STIF_MODE_FP32 = 1
+STIF_FLAG_LOCAL_ENSEMBLE = 0x100
+STIF_NUM_WEIGHT_TENSORS = 26
+STIF_ABI_VERSION = 1
+
+# every symbol include/stif_b200.h declares (tests/test_abi.py checks the .so exports them all)
+EXPORTS = [
+    "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
+    "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_axis_tables",
+    "stif_debug_last_flow", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
+]
+
+
+class StifError(RuntimeError):
+    """A libstif_b200 call failed; the message is ``stif_last_error()``."""
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise StifError(
+            f"{LIB_PATH} not found: build the CUDA library first (__graft_entry__.build()); "
+            "stif_b200 has no CPU or PyTorch fallback")
+    lib = C.CDLL(LIB_PATH)
+    fp, ip, vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_void_p
+    lib.stif_abi_version.restype = C.c_int
+    lib.stif_last_error.restype = C.c_char_p
+    lib.stif_create.argtypes = [C.POINTER(vp), C.c_int]
+    lib.stif_destroy.argtypes = [vp]
+    lib.stif_load_weights.argtypes = [vp, C.POINTER(vp), C.c_int]
+    lib.stif_workspace_bytes.argtypes = [C.c_int] * 7
+    lib.stif_workspace_bytes.restype = C.c_size_t
+    lib.stif_decode.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int,
+                                vp, C.c_size_t, vp, vp]
+    lib.stif_decode_rows.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]
+    lib.stif_decode_host.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, vp]
+    lib.stif_axis_tables.argtypes = [C.c_int, C.c_int, fp, ip, fp, fp]
+    lib.stif_debug_last_flow.argtypes = [vp, fp, C.c_size_t]
+    lib.stif_launch_count.argtypes = [vp]
+    lib.stif_launch_count.restype = C.c_int64
+    lib.stif_profile_enable.argtypes = [vp, C.c_int]
+    lib.stif_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.stif_selftest.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+    for name in EXPORTS:  # fail at import, not at first use, if a symbol is missing
+        getattr(lib, name)
+    if lib.stif_abi_version() != STIF_ABI_VERSION:
+        raise StifError(f"ABI mismatch: library {lib.stif_abi_version()} != binding {STIF_ABI_VERSION}")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != STIF_OK:
+        raise StifError(f"libstif_b200 error {rc}: {lib.stif_last_error().decode(errors='replace')}")
+
+
+def axis_tables(n_lr: int, n_hr: int):
+    """Host-side per-axis query tables (numpy): coord, index, rel, base."""
+    import numpy as np
+
+    coord = np.empty(n_hr, np.float32)
+    index = np.empty(n_hr, np.int32)
+    rel = np.empty(n_hr, np.float32)
+    base = np.empty(n_hr, np.float32)
+    fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    check(lib.stif_axis_tables(n_lr, n_hr, coord.ctypes.data_as(fp), index.ctypes.data_as(ip),
+                               rel.ctypes.data_as(fp), base.ctypes.data_as(fp)))
+    return {"coord": coord, "index": index, "rel": rel, "base": base}
+
+
+def selftest(device: int = 0) -> tuple[int, str]:
+    buf = C.create_string_buffer(8192)
+    rc = lib.stif_selftest(device, buf, len(buf))
+    return rc, buf.value.decode(errors="replace")

@@ -1,0 +1,32 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "stif-continuous-video-representation_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """Path of libstif_b200.so; builds it in-tree if it is missing (nvcc cross-compiles without a GPU)."""
+    so = os.path.join(PKG, "lib", "libstif_b200.so")
+    if not os.path.isfile(so):
+        subprocess.check_call(["bash", os.path.join(PKG, "csrc", "build.sh")])
+    return so
+
+
+@pytest.fixture(scope="session")
+def stif(built_lib):
+    import stif_b200
+    return stif_b200

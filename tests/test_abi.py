@@ -1,0 +1,76 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol include/stif_b200.h declares,
+its host-side axis tables are bit-exact against the torch-generated fixtures, and it fails loudly
+(no CPU fallback) when there is no device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, ROOT
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "stif_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(stif_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    lib = C.CDLL(built_lib)
+    names = _declared_symbols()
+    assert len(names) >= 13
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/stif_b200.h but not exported"
+
+
+def test_binding_lists_the_same_symbols(stif):
+    from stif_b200 import _lib
+    assert sorted(_lib.EXPORTS) == _declared_symbols()
+    assert _lib.lib.stif_abi_version() == 1
+
+
+def test_axis_tables_bit_exact_vs_torch_fixtures(stif):
+    """nearest indices (F.grid_sample) and make_coord axes: the bit-exact contract of the north star."""
+    a = np.load(os.path.join(GOLD, "axis_tables.npz"))
+    from oracle import restate_np as R
+    for n_lr, n_hr in a["pairs"]:
+        t = stif.axis_tables(int(n_lr), int(n_hr))
+        assert np.array_equal(t["index"], a[f"idx_{n_lr}_{n_hr}"]), (n_lr, n_hr)
+        assert np.array_equal(t["coord"], a[f"coord_{n_hr}"]), (n_lr, n_hr)
+        o = R.query_axis_tables(int(n_lr), int(n_hr))
+        assert np.array_equal(t["rel"], o["rel"])
+        assert np.array_equal(t["base"], o["base"])
+
+
+def test_axis_tables_reject_bad_sizes(stif):
+    with pytest.raises(stif.StifError):
+        stif.axis_tables(0, 16)
+
+
+def test_workspace_bytes(stif):
+    from stif_b200._lib import lib
+    assert lib.stif_workspace_bytes(1, 0, 4, 16, 16, 1, 0) == 0
+    bf = lib.stif_workspace_bytes(1, 16, 16, 64, 64, 2, 0)
+    fp = lib.stif_workspace_bytes(1, 16, 16, 64, 64, 2, 1)
+    assert 0 < bf < fp
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
+def test_no_cpu_fallback(stif):
+    from stif_b200._lib import lib
+    h = C.c_void_p()
+    rc = lib.stif_create(C.byref(h), 0)
+    assert rc == -2 and not h
+    assert b"no CPU fallback" in lib.stif_last_error()
+    with pytest.raises(stif.StifError):
+        stif.STIFQueryDecoder()
+    rc, rep = stif.selftest(0)
+    assert rc != 0
+
+
+def test_weight_key_order_matches_fixture_generator(stif):
+    from oracle import synth
+    assert stif.weight_keys() == synth.weight_keys()

@@ -1,0 +1,178 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference-generated
+fixtures.  GPU box only (-m gpu); nothing here reads /root/reference.
+
+Bars (BASELINE.json north_star): RGB max-abs <= 1e-4 in fp32 mode, <= 2e-2 in bf16 mode,
+PSNR delta <= 0.05 dB; nearest indices / rel bit-exact (host tables: tests/test_abi.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD
+from oracle import port_torch, synth
+from oracle import restate_np as R
+from oracle.make_goldens import CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def decoders(stif):
+    cache = {}
+
+    def get(wseed, stress, mode):
+        key = (wseed, stress, mode)
+        if key not in cache:
+            d = stif.STIFQueryDecoder(0, mode=mode)
+            d.load_weights(synth.make_weights(wseed, stress))
+            cache[key] = d
+        return cache[key]
+    return get
+
+
+def _run(dec, lat, fr, times, scale):
+    out = dec.decode_stacked(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), _times(times), scale)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _times(times):
+    t = np.asarray(times, dtype=np.float32)
+    return [torch.tensor(r, dtype=torch.float32).view(-1, 1) for r in t] if t.ndim == 2 else [float(x) for x in t]
+
+
+def test_tcgen05_selftest(stif):
+    rc, report = stif.selftest(0)
+    print(report)
+    assert rc == 0, report
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_cases(name, mode, decoders):
+    cfg = CASES[name]
+    g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+    lat, fr = synth.make_inputs(cfg["iseed"], cfg["B"], cfg["H"], cfg["W"], cfg["latent_std"])
+    dec = decoders(cfg["wseed"], cfg["stress"], mode)
+    rgb = _run(dec, lat, fr, cfg["times"], cfg["scale"])
+    assert rgb.shape == g["rgb"].shape
+    err = np.abs(rgb - g["rgb"]).max()
+    print(f"{name} {mode}: rgb max-abs {err:.3e}")
+    assert err <= TOL[mode]
+    # flow of the last slab (HR-pixel units) against the reference's flow_imnet output
+    T, B = len(cfg["times"]), cfg["B"]
+    HH, WW = rgb.shape[-2:]
+    flow = dec.last_flow(HH, WW)
+    ref = g[f"flow_{T - 1}"][(B - 1) * HH * WW:]
+    ferr = np.abs(flow - ref).max()
+    print(f"{name} {mode}: flow max-abs {ferr:.3e} px (|flow| max {np.abs(ref).max():.1f})")
+    assert ferr <= (2e-3 if mode == "fp32" else 0.5)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("stress", [False, True])
+def test_config1(stress, mode, decoders):
+    """BASELINE.json config 1: 64x64 latent -> 256x256, t = i/8, against the reference's own output sample."""
+    g = np.load(os.path.join(GOLD, f"config1_{'stress' if stress else 'init'}.npz"))
+    lat, fr = synth.make_inputs(0, 1, 64, 64, 0.05)
+    rgb = _run(decoders(0, stress, mode), lat, fr, [i / 8.0 for i in range(8)], None)
+    err = np.abs(rgb[:, :, :, 1::5, 2::5] - g["rgb_sub"]).max()
+    print(f"config1 stress={stress} {mode}: max-abs {err:.3e}")
+    assert err <= TOL[mode]
+    assert np.abs(rgb.mean(axis=(1, 2, 3, 4)) - g["mean"]).max() <= TOL[mode] / 10
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_config3_noninteger_scale_vs_oracle(mode, decoders):
+    """x6.5 (exact .5 ties in the nearest index), 8 intermediate timesteps k/9, 64x64 latent -> 416x416."""
+    lat, fr = synth.smooth_inputs(5, 1, 64, 64, 0.05)
+    w = synth.make_weights(1, True)
+    times = [k / 9.0 for k in range(1, 9)]
+    scale = (int(6.5 * 64), int(6.5 * 64))
+    ref = port_torch.decode(lat, fr, w, times, scale).numpy()
+    rgb = _run(decoders(1, True, mode), lat, fr, times, scale)
+    err = np.abs(rgb - ref).max()
+    psnr = R.psnr255(rgb, ref)
+    print(f"config3 {mode}: max-abs {err:.3e} PSNR(new,ref) {psnr:.1f} dB")
+    assert err <= TOL[mode]
+    assert psnr >= 50.0
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_psnr_delta_against_pseudo_ground_truth(mode, decoders):
+    """|PSNR(new,GT) - PSNR(ref,GT)| <= 0.05 dB with GT = the reference output + noise-free offset image.
+    (utils/util.py:140-151 PSNR on clamp(0,1)*255.)"""
+    lat, fr = synth.smooth_inputs(7, 1, 48, 40, 0.05)
+    w = synth.make_weights(2, True)
+    ref = port_torch.decode(lat, fr, w, [0.3], None).numpy()
+    rng = np.random.default_rng(0)
+    gt = ref + rng.normal(0, 0.02, ref.shape).astype(np.float32)      # a 34 dB "ground truth"
+    rgb = _run(decoders(2, True, mode), lat, fr, [0.3], None)
+    d = abs(R.psnr255(rgb, gt) - R.psnr255(ref, gt))
+    print(f"{mode}: PSNR delta {d:.4f} dB")
+    assert d <= 0.05
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_properties_at_config2_size(mode, decoders):
+    """Size-independent properties at BASELINE.json's config-2 size (270x480 latent -> 1080x1920, t in {0, 0.5}):
+    determinism, independence of timesteps, row-band decode == full decode, fp32/bf16 agreement."""
+    lat, fr = synth.smooth_inputs(11, 1, 270, 480, 0.05)
+    dec = decoders(0, True, mode)
+    a = _run(dec, lat, fr, [0.0, 0.5], None)
+    assert a.shape == (2, 1, 3, 1080, 1920) and np.isfinite(a).all()
+    b = _run(dec, lat, fr, [0.0, 0.5], None)
+    assert np.array_equal(a, b)                                        # deterministic
+    c = _run(dec, lat, fr, [0.5], None)
+    assert np.array_equal(a[1], c[0])                                  # slabs are independent (Sakuya_arch_test.py:380)
+    latc, frc = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    band = torch.zeros((1, 1, 3, 1080, 1920), device="cuda")
+    dec.decode_stacked(latc, frc, [0.5], None, rows=(300, 420), halo=64, out=band)
+    torch.cuda.synchronize()
+    assert np.array_equal(band.cpu().numpy()[0, 0, :, 300:420], a[1, 0, :, 300:420])
+    assert float(band[0, 0, :, :300].abs().max()) == 0.0
+    other = _run(decoders(0, True, "fp32" if mode == "bf16" else "bf16"), lat, fr, [0.0, 0.5], None)
+    err = np.abs(a - other).max()
+    print(f"config2 size: fp32 vs bf16 max-abs {err:.3e}, PSNR {R.psnr255(a, other):.1f} dB")
+    assert err <= 2e-2
+
+
+def test_band_halo_violation_is_reported(decoders, stif):
+    lat, fr = synth.make_inputs(1, 1, 16, 16, 0.05)
+    dec = decoders(1, True, "fp32")                                   # stress weights: flows of ~13 px
+    out = torch.zeros((1, 1, 3, 104, 104), device="cuda")
+    with pytest.raises(stif.StifError, match="halo"):
+        dec.decode_stacked(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), [0.5], (104, 104),
+                           rows=(40, 60), halo=1, out=out)
+
+
+def test_forward_feat_coord_cell_adapter(decoders):
+    """north-star surface forward(feat, coord, cell): (y,x,t) rasters + cell=(2/HH, 2/WW, .)."""
+    lat, fr = synth.make_inputs(0, 1, 16, 16, 0.05)
+    dec = decoders(0, False, "fp32")
+    HH = WW = 64
+    ay, ax = R.clamp_axis(R.make_axis(HH)), R.clamp_axis(R.make_axis(WW))
+    yy, xx = np.meshgrid(ay, ax, indexing="ij")
+    slabs = [np.stack([yy, xx, np.full_like(yy, t)], -1).reshape(-1, 3) for t in (0.0, 0.375)]
+    coord = torch.from_numpy(np.concatenate(slabs, 0)[None].astype(np.float32))
+    cell = torch.tensor([2.0 / HH, 2.0 / WW, 0.5]).expand_as(coord).contiguous()
+    feat = (torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda())
+    out = dec(feat, coord, cell).cpu().numpy()                        # [1, 2*Q, 3]
+    g = np.load(os.path.join(GOLD, "case_x4_init.npz"))["rgb"]       # [2,1,3,64,64]
+    ref = np.concatenate([g[t, 0].reshape(3, -1).T for t in range(2)], 0)[None]
+    assert np.abs(out - ref).max() <= 1e-4
+    bad = coord.clone()
+    bad[0, 5, 1] += 0.01
+    with pytest.raises(ValueError, match="raster"):
+        dec(feat, bad, cell)
+
+
+def test_host_entry_point(decoders):
+    lat, fr = synth.make_inputs(0, 1, 16, 16, 0.05)
+    dec = decoders(0, False, "fp32")
+    out = dec.decode_host(lat, fr, [0.0, 0.375], None).numpy()
+    g = np.load(os.path.join(GOLD, "case_x4_init.npz"))["rgb"]
+    assert np.abs(out - g).max() <= 1e-4
