@@ -1,20 +1,23 @@
 // kernels_tc.cu -- the fused bf16 tensor-core path of the STIF query decoder (STIF_MODE_BF16).
 //
-// Two persistent kernels per (t, b) slab, one CTA per SM, 256 threads = two independent
-// "workgroups" (WG, 4 warps each) that each own a 128-query tile and half of tensor memory:
+// Three kernels, all persistent (one CTA per SM), all tcgen05 / TMEM:
 //
+//   K0  latent projection (per frame pair, t-independent): tab[texel, 256] = W_tab . [latent; frames]
+//       -- the hoisted first layers of the three SIRENs.
 //   K1  stage A + B  (reference Sakuya_arch_test.py:382-422): nearest gather of the projected latent
 //       -> feat_imnet trunk -> composed last layer writes the projected HR table (Q1|Q2, fp16) ->
 //       + bilinear gather of TB -> flow_imnet trunk -> flow (fp32).
 //   K2  stage C + D + E (warplayer.py:25-39, :424-458): warp positions from the flow, four bilinear
 //       gathers (Q1@g1, Q2@g2, TE1@g1, TE2@g2) -> encode_imnet trunk -> RGB (fp32 planar).
 //
-// Per tile every MLP layer is a chain of tcgen05.mma (M=128 queries, N=64 output chunk, K=16 per
-// instruction, bf16 x bf16 -> fp32 in TMEM).  Weights stay resident in shared memory for the
-// whole kernel (bulk-TMA loaded once); activations never leave the SM: the epilogue warps read
-// an accumulator chunk (tcgen05.ld), apply bias + sine (MUFU), round to bf16 and write it back
-// to TMEM as the next layer's A operand (tcgen05.st, "TS" MMA form).  The 256->4 (flow) and
-// 256->3 (RGB) output layers run on the FMA pipe in fp32 straight from the sine outputs.
+// K1/K2: 512 threads = two "workgroups" (WG, 8 warps) that each own a 128-query tile and half of
+// tensor memory.  Per tile every MLP layer is a chain of tcgen05.mma (M=128 queries, N=64 output
+// chunk, K=16 per instruction, bf16 x bf16 -> fp32 in TMEM).  Weights stay resident in shared
+// memory for the whole kernel (bulk-TMA loaded once); activations never leave the SM: the
+// epilogue warps read an accumulator chunk (tcgen05.ld), apply bias + sine (MUFU), round to bf16
+// and write it back to TMEM as the next layer's A operand (tcgen05.st, "TS" MMA form).  The
+// 256->4 (flow) and 256->3 (RGB) output layers run on the FMA pipe in fp32 (packed FFMA2) straight
+// from the sine outputs.  Two warps share each TMEM lane quarter and split a chunk's 64 columns.
 //
 // TMEM map of one WG (256 columns): A-area [0,128) = up to 256 bf16 activations per query;
 // D-area [128,256) = two 64-column fp32 accumulator slots used as a ring (MMA of chunk c+1
@@ -40,17 +43,20 @@ constexpr uint32_t kColD = 128;   // two accumulator slots: [128,192), [192,256)
 
 // ---- shared-memory images (bytes) ----------------------------------------------------------
 constexpr uint32_t kW64x64 = 64 * 64 * 2, kW256x64 = 256 * 64 * 2, kW192x256 = 192 * 256 * 2, kW256x256 = 256 * 256 * 2;
-// K1: F1 | F2 | F3(composed 192x256) | L1 | L2
+// K1: F1 | F2 | F3(composed 192x256) | L1 | L2 | partial-sum exchange
 constexpr uint32_t k1F1 = 0, k1F2 = k1F1 + kW64x64, k1F3 = k1F2 + kW256x64, k1L1 = k1F3 + kW192x256,
                    k1L2 = k1L1 + kW64x64, k1WBytes = k1L2 + kW256x64;
-constexpr uint32_t k1Bars = k1WBytes, k1Smem = k1Bars + 128 + 1024;
-// K2: E1 | E2 | E3 | A0[2] | tap staging[8 warps x 2 KB]
+constexpr uint32_t k1Part = k1WBytes, k1Bars = k1Part + 2 * 128 * 16, k1Smem = k1Bars + 128;
+// K2: E1 | E2 | E3 | A0[2 WGs] | tap staging [16 warps x 1536 B] (reused for the partial-sum exchange)
 constexpr uint32_t k2E1 = 0, k2E2 = k2E1 + kW64x64, k2E3 = k2E2 + kW256x64, k2WBytes = k2E3 + kW256x256;
-constexpr uint32_t k2A0 = k2WBytes, k2Taps = k2A0 + 2 * 16384, k2Bars = k2Taps + 8 * 2048, k2Smem = k2Bars + 128 + 1024;
-static_assert(k2A0 % 1024 == 0 && k1F3 % 1024 == 0 && k1L1 % 1024 == 0 && k2E3 % 1024 == 0, "SW128 tiles need 1024 B alignment");
-static_assert(k2Smem <= 232448 && k1Smem <= 232448, "exceeds 227 KB of shared memory");
+constexpr uint32_t k2A0 = k2WBytes, k2Taps = k2A0 + 2 * 16384, k2Bars = k2Taps + 16 * 1536, k2Smem = k2Bars + 128;
+// K0: A tile (4 K-blocks x 128 rows) | W_tab (4 K-blocks x 256 rows)
+constexpr uint32_t k0A = 0, k0B = 4 * 128 * 128, k0WBytes = 4 * 256 * 128, k0Bars = k0B + k0WBytes, k0Smem = k0Bars + 128;
+static_assert(k2A0 % 1024 == 0 && k1F3 % 1024 == 0 && k1L1 % 1024 == 0 && k2E3 % 1024 == 0 && k0B % 1024 == 0,
+              "SW128 tiles need 1024 B alignment");
+static_assert(k2Smem <= 232448 && k1Smem <= 232448 && k0Smem <= 232448, "exceeds 227 KB of shared memory");
 
-struct K1Consts {
+struct alignas(16) K1Consts {
   float cA[64];       // feat_imnet L0: w_t * t + b        (per launch)
   float a_rel[128];   // feat_imnet L0: (rel_y, rel_x) columns, [c][2]
   float f1_b[64], f2_b[256], f3_b[192];
@@ -58,7 +64,7 @@ struct K1Consts {
   float l1_b[64], l2_b[256];
   float l3_w[4 * 256], l3_b[4];
 };
-struct K2Consts {
+struct alignas(16) K2Consts {
   float cE[64];       // encode_imnet L0: w_t * t + b      (per launch)
   float e1_b[64], e2_b[256], e3_b[256];
   float e4_w[3 * 256], e4_b[4];
@@ -85,6 +91,15 @@ struct K2Params {
   int band_lo, band_hi, band_mode;
   int* flag;
 };
+struct K0Params {
+  const float* latent;  // [192, HW]
+  const float* frames;  // [6, HW]
+  __half* tab;          // [HW, 256]
+  const uint8_t* wimg;  // W_tab, bf16, [256 x 256 (K padded)] SW128 image
+  long HW;
+};
+
+extern __shared__ __align__(1024) uint8_t smem[];
 
 // ---- workgroup context -----------------------------------------------------------------------
 struct WgCtx {
@@ -92,10 +107,10 @@ struct WgCtx {
   uint32_t lane_addr;  // same + this warp's lane quarter (for tcgen05.ld/st)
   uint64_t* full;      // two mbarriers: accumulator slot s is complete
   uint32_t n_issued, n_waited;
-  int wg, tid_wg;
+  int wg, tid_wg, row, colhalf;
 };
 
-__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
 
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   long long t0 = 0;
@@ -127,13 +142,14 @@ __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_smem, uint32_t
   ++cx.n_issued;
 }
 
-// Wait for the oldest outstanding chunk; returns the lane-adjusted TMEM address of its accumulator slot.
+// Wait for the oldest outstanding chunk; returns the lane-adjusted TMEM address of this thread's
+// 32-column half of its accumulator slot.
 __device__ __forceinline__ uint32_t wait_chunk(WgCtx& cx) {
   const uint32_t slot = cx.n_waited & 1, parity = (cx.n_waited >> 1) & 1;
   mbar_wait_or_trap(&cx.full[slot], parity);
   ++cx.n_waited;
   tc_fence_after();
-  return cx.lane_addr + kColD + slot * 64;
+  return cx.lane_addr + kColD + slot * 64 + cx.colhalf * 32;
 }
 
 // One MLP layer: NC output chunks of 64.  Preconditions: the A operand is complete and a WG barrier
@@ -157,44 +173,38 @@ __device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_smem, uint32_t a
   }
 }
 
-// ---- epilogues (thread = query row; 64 accumulator columns per chunk) ---------------------------
-// act = sin(acc + bias) -> bf16 -> TMEM A operand at column dst (32 columns)
+__device__ __forceinline__ float2 ldc2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+
+// ---- epilogues (thread = query row x 32 of the chunk's 64 accumulator columns) --------------------
+// act = sin(acc + bias) -> bf16 -> TMEM A operand (16 columns at dst)
 __device__ __forceinline__ void epi_sin_to_tmem(uint32_t src, uint32_t dst, const float* __restrict__ bias) {
-  uint32_t v0[32], v1[32], pk[16];
-  tmem_ld32(src, v0);
-  tmem_ld32(src + 32, v1);
+  uint32_t v[32], pk[16];
+  tmem_ld32(src, v);
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    pk[j] = pack_bf16x2(fast_sin(__uint_as_float(v0[2 * j]) + bias[2 * j]), fast_sin(__uint_as_float(v0[2 * j + 1]) + bias[2 * j + 1]));
+  for (int j = 0; j < 16; ++j) {
+    const float2 a = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), ldc2(bias + 2 * j));
+    pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
+  }
   tmem_st16(dst, pk);
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    pk[j] = pack_bf16x2(fast_sin(__uint_as_float(v1[2 * j]) + bias[32 + 2 * j]),
-                        fast_sin(__uint_as_float(v1[2 * j + 1]) + bias[32 + 2 * j + 1]));
-  tmem_st16(dst + 16, pk);
   tmem_st_wait();
 }
 
-// act = sin(acc + bias) kept in fp32 and contracted with the NOUT x 256 output layer on the FMA pipe
+// act = sin(acc + bias) kept in fp32 and contracted with the NOUT x 256 output layer on the FMA pipe.
+// acc[k] holds (even-column, odd-column) partial sums.
 template <int NOUT>
 __device__ __forceinline__ void epi_sin_fma(uint32_t src, const float* __restrict__ bias, const float* __restrict__ w,
-                                            float (&acc)[NOUT]) {
-  uint32_t v0[32], v1[32];
-  tmem_ld32(src, v0);
-  tmem_ld32(src + 32, v1);
+                                            float2 (&acc)[NOUT]) {
+  uint32_t v[32];
+  tmem_ld32(src, v);
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float s = fast_sin(__uint_as_float(v0[j]) + bias[j]);
+  for (int j = 0; j < 16; ++j) {
+    float2 s = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), ldc2(bias + 2 * j));
+    s.x = fast_sin(s.x);
+    s.y = fast_sin(s.y);
 #pragma unroll
-    for (int k = 0; k < NOUT; ++k) acc[k] = fmaf(w[k * 256 + j], s, acc[k]);
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float s = fast_sin(__uint_as_float(v1[j]) + bias[32 + j]);
-#pragma unroll
-    for (int k = 0; k < NOUT; ++k) acc[k] = fmaf(w[k * 256 + 32 + j], s, acc[k]);
+    for (int k = 0; k < NOUT; ++k) acc[k] = fma2(s, ldc2(w + k * 256 + 2 * j), acc[k]);
   }
 }
 
@@ -202,75 +212,60 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&v));
-}
 
-// acc + bias -> fp16 -> 128 bytes of the projected HR table
+// acc + bias -> fp16 -> 64 bytes of the projected HR table
 __device__ __forceinline__ void epi_store_qtab(uint32_t src, const float* __restrict__ bias, __half* dst, bool valid) {
-  uint32_t v0[32], v1[32];
-  tmem_ld32(src, v0);
-  tmem_ld32(src + 32, v1);
+  uint32_t v[32];
+  tmem_ld32(src, v);
   tmem_ld_wait();
   if (!valid) return;
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    uint4 o;
-    o.x = pack_half2(__uint_as_float(v0[8 * j + 0]) + bias[8 * j + 0], __uint_as_float(v0[8 * j + 1]) + bias[8 * j + 1]);
-    o.y = pack_half2(__uint_as_float(v0[8 * j + 2]) + bias[8 * j + 2], __uint_as_float(v0[8 * j + 3]) + bias[8 * j + 3]);
-    o.z = pack_half2(__uint_as_float(v0[8 * j + 4]) + bias[8 * j + 4], __uint_as_float(v0[8 * j + 5]) + bias[8 * j + 5]);
-    o.w = pack_half2(__uint_as_float(v0[8 * j + 6]) + bias[8 * j + 6], __uint_as_float(v0[8 * j + 7]) + bias[8 * j + 7]);
-    d4[j] = o;
-  }
+    uint32_t o[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 o;
-    o.x = pack_half2(__uint_as_float(v1[8 * j + 0]) + bias[32 + 8 * j + 0], __uint_as_float(v1[8 * j + 1]) + bias[32 + 8 * j + 1]);
-    o.y = pack_half2(__uint_as_float(v1[8 * j + 2]) + bias[32 + 8 * j + 2], __uint_as_float(v1[8 * j + 3]) + bias[32 + 8 * j + 3]);
-    o.z = pack_half2(__uint_as_float(v1[8 * j + 4]) + bias[32 + 8 * j + 4], __uint_as_float(v1[8 * j + 5]) + bias[32 + 8 * j + 5]);
-    o.w = pack_half2(__uint_as_float(v1[8 * j + 6]) + bias[32 + 8 * j + 6], __uint_as_float(v1[8 * j + 7]) + bias[32 + 8 * j + 7]);
-    d4[4 + j] = o;
+    for (int e = 0; e < 4; ++e) {
+      const float2 a = add2(make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])),
+                            ldc2(bias + 8 * j + 2 * e));
+      o[e] = pack_half2(a.x, a.y);
+    }
+    d4[j] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
 // f0 = sin(F + g) -> bf16 -> TMEM (g already holds bilinear(TB) + time constant + composed bias)
-__device__ __forceinline__ void epi_flow_first_layer(uint32_t src, uint32_t dst, const float (&g)[64]) {
-  uint32_t v0[32], v1[32], pk[16];
-  tmem_ld32(src, v0);
-  tmem_ld32(src + 32, v1);
+__device__ __forceinline__ void epi_flow_first_layer(uint32_t src, uint32_t dst, const float (&g)[32]) {
+  uint32_t v[32], pk[16];
+  tmem_ld32(src, v);
   tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
-    pk[j] = pack_bf16x2(fast_sin(__uint_as_float(v0[2 * j]) + g[2 * j]), fast_sin(__uint_as_float(v0[2 * j + 1]) + g[2 * j + 1]));
+  for (int j = 0; j < 16; ++j) {
+    const float2 a = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), make_float2(g[2 * j], g[2 * j + 1]));
+    pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
+  }
   tmem_st16(dst, pk);
-#pragma unroll
-  for (int j = 0; j < 16; ++j)
-    pk[j] = pack_bf16x2(fast_sin(__uint_as_float(v1[2 * j]) + g[32 + 2 * j]), fast_sin(__uint_as_float(v1[2 * j + 1]) + g[32 + 2 * j + 1]));
-  tmem_st16(dst + 16, pk);
   tmem_st_wait();
 }
 
-// ---- common prologue / epilogue of both kernels ---------------------------------------------------
+// ---- common prologue / epilogue of the kernels -----------------------------------------------------
 struct CtaSetup {
-  uint8_t* smem;
   uint64_t* bars;  // [0] weights landed, [1,2] WG0 slots, [3,4] WG1 slots
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ CtaSetup cta_prologue(uint8_t* smem_raw, uint32_t bars_off, const uint8_t* wimg, uint32_t wbytes) {
+__device__ __forceinline__ CtaSetup cta_prologue(uint32_t bars_off, uint32_t w_off, const uint8_t* wimg, uint32_t wbytes,
+                                                 uint32_t tmem_cols) {
   CtaSetup s;
-  s.smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  s.bars = reinterpret_cast<uint64_t*>(s.smem + bars_off);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s.bars + 8);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();   // SW128 operands assume a 1024-byte aligned window
+  s.bars = reinterpret_cast<uint64_t*>(smem + bars_off);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bars_off + 64);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(&s.bars[0], 1);
-    for (int i = 1; i <= 4; ++i) mbar_init(&s.bars[i], 1);
+    for (int i = 0; i <= 4; ++i) mbar_init(&s.bars[i], 1);
     fence_mbar_init();
   }
   if (tid < 32) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -280,46 +275,124 @@ __device__ __forceinline__ CtaSetup cta_prologue(uint8_t* smem_raw, uint32_t bar
     mbar_arrive_expect_tx(&s.bars[0], wbytes);
     for (uint32_t off = 0; off < wbytes; off += 32768) {
       const uint32_t n = min(32768u, wbytes - off);
-      bulk_copy_g2s(s.smem + off, wimg + off, n, &s.bars[0]);
+      bulk_copy_g2s(smem + w_off + off, wimg + off, n, &s.bars[0]);
     }
   }
   s.tmem_base = *tmem_slot;
-  mbar_wait_or_trap(&s.bars[0], 0);
   return s;
 }
 
-__device__ __forceinline__ void cta_epilogue(uint32_t tmem_base) {
+__device__ __forceinline__ void cta_epilogue(uint32_t tmem_base, uint32_t tmem_cols) {
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x < 32) tmem_dealloc(tmem_base, 512);
+  if (threadIdx.x < 32) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   WgCtx cx;
   const int tid = threadIdx.x;
-  cx.wg = tid >> 7;
-  cx.tid_wg = tid & 127;
+  cx.wg = tid >> 8;
+  cx.tid_wg = tid & 255;
+  const int warp_in_wg = cx.tid_wg >> 5;
+  const int quarter = warp_in_wg & 3;        // == (global warp id) % 4 : the TMEM lane quarter this warp may access
+  cx.colhalf = warp_in_wg >> 2;
+  cx.row = quarter * 32 + (tid & 31);
   cx.tmem = s.tmem_base + (uint32_t)cx.wg * 256u;
-  cx.lane_addr = cx.tmem + ((uint32_t)(cx.tid_wg & ~31) << 16);
+  cx.lane_addr = cx.tmem + ((uint32_t)(quarter * 32) << 16);
   cx.full = s.bars + 1 + 2 * cx.wg;
   cx.n_issued = cx.n_waited = 0;
   return cx;
 }
 
 // =================================================================================================
+// K0: latent projection  tab[HW,256] (fp16) = [latent(192) ; frames(6)]^T  W_tab^T      (bf16 MMA)
+// =================================================================================================
+__global__ void __launch_bounds__(256, 1) k0_project_kernel(const __grid_constant__ K0Params p) {
+  const CtaSetup s = cta_prologue(k0Bars, k0B, p.wimg, k0WBytes, 256);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = tid & 127, khalf = tid >> 7;
+  const long ntiles = (p.HW + kTile - 1) / kTile;
+  const uint32_t a_sm = smem_u32(smem + k0A), b_sm = smem_u32(smem + k0B);
+  // K index 200..207 (group 25) is padding: zero it once (B is zero there too, but 0 * garbage could be NaN)
+  if (khalf == 1) *reinterpret_cast<uint4*>(smem + k0A + 3 * 16384 + sw128_offset(row, 8)) = make_uint4(0, 0, 0, 0);
+  mbar_wait_or_trap(&s.bars[0], 0);
+  uint32_t phase = 0;
+  for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long m = min(tile * kTile + row, p.HW - 1);
+    // ---- A tile: thread = (texel row, half of the channel groups); 8 channels -> one 16-byte smem chunk
+#pragma unroll 1
+    for (int gg = 0; gg < 13; ++gg) {
+      const int g8 = khalf * 13 + gg;      // channel group: channels [8 g8, 8 g8 + 8)
+      if (g8 >= 25) break;
+      float v[8];
+      if (g8 < 24) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(p.latent + (long)(g8 * 8 + e) * p.HW + m);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) v[e] = __ldg(p.frames + (long)e * p.HW + m);
+        v[6] = v[7] = 0.f;
+      }
+      const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(smem + k0A + (g8 >> 3) * 16384 + sw128_offset(row, (g8 & 7) * 8)) = o;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, 256);
+      for (int j = 0; j < 13; ++j)    // K = 208 = 13 x 16
+        umma_ss(s.tmem_base, make_desc_sw128(a_sm + (j >> 2) * 16384) + 2 * (j & 3), make_desc_sw128(b_sm + (j >> 2) * 32768) + 2 * (j & 3),
+                idesc, j > 0);
+      umma_commit(&s.bars[1]);
+    }
+    mbar_wait_or_trap(&s.bars[1], phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: warp = (lane quarter, column half); thread = one texel row, 128 channels
+    {
+      const int quarter = warp & 3, colhalf = warp >> 2;
+      const long texel = tile * kTile + quarter * 32 + lane;
+      const uint32_t src = s.tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(src + c * 32, v);
+        tmem_ld_wait();
+        if (texel < p.HW) {
+          uint4* dst = reinterpret_cast<uint4*>(p.tab + texel * 256 + colhalf * 128 + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_half2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                pack_half2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                pack_half2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                pack_half2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  cta_epilogue(s.tmem_base, 256);
+}
+
+// =================================================================================================
 // K1: stage A + B
 // =================================================================================================
-__global__ void __launch_bounds__(256, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const CtaSetup s = cta_prologue(smem_raw, k1Bars, p.wimg, k1WBytes);
-  WgCtx cx = make_wg(s);
-  const uint32_t wsm = smem_u32(s.smem);
+// CH = this thread's column half (compile-time so that every bias / weight index is an immediate
+// constant-bank operand instead of a per-thread LDC)
+template <int CH>
+__device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& s, WgCtx& cx) {
+  const uint32_t wsm = smem_u32(smem);
   const Geometry& g = p.g;
   const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
   const uint4* __restrict__ tab4 = reinterpret_cast<const uint4*>(p.tab);  // 32 uint4 per texel
+  float4* part = reinterpret_cast<float4*>(smem + k1Part) + cx.wg * 128;
+  constexpr int ch0 = CH * 32;   // this thread's 32 channels of every 64-wide vector
 
   for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
-    const long q = p.q_begin + tile * kTile + cx.tid_wg;
+    const long q = p.q_begin + tile * kTile + cx.row;
     const bool valid = q < p.q_end;
     const long qc = valid ? q : p.q_end - 1;
     const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
@@ -329,26 +402,22 @@ __global__ void __launch_bounds__(256, 1) k1_stage_ab_kernel(const __grid_consta
       const int iy = g.y.idx[jy], ix = g.x.idx[jx];
       const float rely = g.y.rel[jy], relx = g.x.rel[jx];
       const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
-      const uint4* ta = tab4 + (inb ? ((long)iy * g.W + ix) : 0) * 32;
-      const float mask = inb ? 1.f : 0.f;
+      const uint4* ta = tab4 + (inb ? ((long)iy * g.W + ix) : 0) * 32 + CH * 4;
+      uint32_t pk[16];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t pk[16];
+      for (int j = 0; j < 4; ++j) {
+        uint4 v = __ldg(ta + j);
+        if (!inb) v = make_uint4(0, 0, 0, 0);
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint4 v = __ldg(ta + half * 4 + j);
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = half * 32 + j * 8 + e * 2;
-            const float2 f = unpack_half2(w4[e]);
-            const float a0 = fmaf(f.x, mask, fmaf(rely, p.c.a_rel[2 * c], fmaf(relx, p.c.a_rel[2 * c + 1], p.c.cA[c])));
-            const float a1 = fmaf(f.y, mask, fmaf(rely, p.c.a_rel[2 * c + 2], fmaf(relx, p.c.a_rel[2 * c + 3], p.c.cA[c + 1])));
-            pk[j * 4 + e] = pack_bf16x2(fast_sin(a0), fast_sin(a1));
-          }
+        for (int e = 0; e < 4; ++e) {
+          const int c = ch0 + j * 8 + e * 2;
+          const float b0 = fmaf(rely, p.c.a_rel[2 * c], fmaf(relx, p.c.a_rel[2 * c + 1], p.c.cA[c]));
+          const float b1 = fmaf(rely, p.c.a_rel[2 * c + 2], fmaf(relx, p.c.a_rel[2 * c + 3], p.c.cA[c + 1]));
+          pk[j * 4 + e] = pack_bf16x2(fast_sin(add_f16((uint16_t)(w4[e] & 0xFFFF), b0)), fast_sin(add_f16((uint16_t)(w4[e] >> 16), b1)));
         }
-        tmem_st16(cx.lane_addr + kColAin + half * 16, pk);
       }
+      tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
       tmem_st_wait();
     }
     tc_fence_before();
@@ -356,164 +425,198 @@ __global__ void __launch_bounds__(256, 1) k1_stage_ab_kernel(const __grid_consta
 
     // ---- feat_imnet hidden layers
     run_layer<1>(cx, 0, kColAin, wsm + k1F1, 64, 4, [](int) { return 0; },
-                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin, p.c.f1_b); });
-    run_layer<4>(cx, 0, kColAin, wsm + k1F2, 256, 4, [](int i) { return i; },
-                 [&](int i, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i, p.c.f2_b + 64 * i); });
+                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0); });
+    run_layer<4>(cx, 0, kColAin, wsm + k1F2, 256, 4, [](int i) { return i; }, [&](int i, uint32_t d) {
+      epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0);
+    });
 
     // ---- stage B gather, issued before the composed layer so its latency hides behind the MMAs:
     //      gB = bilinear(TB; query position) + cB + composed bias of F                  (:410-418)
-    float gB[64];
+    float gB[32];
     {
       const Taps tp = make_taps_tables(g, jy, jx);
+      uint16_t wq[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float acc[8];
+      for (int k = 0; k < 4; ++k) wq[k] = __half_as_ushort(__float2half_rn(tp.w[k]));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = p.c.cB[8 * j + e] + p.c.f3_b[8 * j + e];
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gB[8 * j + e] = p.c.cB[ch0 + 8 * j + e] + p.c.f3_b[ch0 + 8 * j + e];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint4 v = __ldg(tab4 + (long)tp.off[k] * 32 + 8 + j);
+          const uint4 v = __ldg(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + j);
           const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 f = unpack_half2(w4[e]);
-            acc[2 * e] = fmaf(tp.w[k], f.x, acc[2 * e]);
-            acc[2 * e + 1] = fmaf(tp.w[k], f.y, acc[2 * e + 1]);
+            gB[8 * j + 2 * e] = fma_f16((uint16_t)(w4[e] & 0xFFFF), wq[k], gB[8 * j + 2 * e]);
+            gB[8 * j + 2 * e + 1] = fma_f16((uint16_t)(w4[e] >> 16), wq[k], gB[8 * j + 2 * e + 1]);
           }
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) gB[8 * j + e] = acc[e];
       }
     }
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
-    run_layer<3>(cx, 0, kColA, wsm + k1F3, 192, 16, [](int i) { return i == 2 ? 0 : i + 1; },
-                 [&](int i, uint32_t d) {
-                   if (i < 2) epi_store_qtab(d, p.c.f3_b + 64 * (i + 1), p.qtab + qc * 128 + 64 * i, valid);
-                   else epi_flow_first_layer(d, cx.lane_addr + kColAin, gB);
-                 });
+    run_layer<3>(cx, 0, kColA, wsm + k1F3, 192, 16, [](int i) { return i == 2 ? 0 : i + 1; }, [&](int i, uint32_t d) {
+      if (i < 2) epi_store_qtab(d, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid);
+      else epi_flow_first_layer(d, cx.lane_addr + kColAin + CH * 16, gB);
+    });
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
     run_layer<1>(cx, 0, kColAin, wsm + k1L1, 64, 4, [](int) { return 0; },
-                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin, p.c.l1_b); });
-    float fl[4] = {p.c.l3_b[0], p.c.l3_b[1], p.c.l3_b[2], p.c.l3_b[3]};
+                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0); });
+    float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4>(cx, 0, kColAin, wsm + k1L2, 256, 4, [](int i) { return i; },
-                 [&](int i, uint32_t d) { epi_sin_fma<4>(d, p.c.l2_b + 64 * i, p.c.l3_w + 64 * i, fl); });
-    if (valid) reinterpret_cast<float4*>(p.flow)[q] = make_float4(fl[0], fl[1], fl[2], fl[3]);
+                 [&](int i, uint32_t d) { epi_sin_fma<4>(d, p.c.l2_b + 64 * i + ch0, p.c.l3_w + 64 * i + ch0, fl); });
+    // combine the two column halves and store
+    const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
+    if (CH == 1) part[cx.row] = mine;
+    wg_barrier(cx.wg);
+    if (CH == 0 && valid) {
+      const float4 o = part[cx.row];
+      reinterpret_cast<float4*>(p.flow)[q] =
+          make_float4(mine.x + o.x + p.c.l3_b[0], mine.y + o.y + p.c.l3_b[1], mine.z + o.z + p.c.l3_b[2], mine.w + o.w + p.c.l3_b[3]);
+    }
   }
-  cta_epilogue(s.tmem_base);
+}
+
+__global__ void __launch_bounds__(512, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
+  const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
+  WgCtx cx = make_wg(s);
+  mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.colhalf == 0) k1_tile_loop<0>(p, s, cx);
+  else k1_tile_loop<1>(p, s, cx);
+  cta_epilogue(s.tmem_base, 512);
 }
 
 // =================================================================================================
 // K2: stage C + D + E
 // =================================================================================================
-// Warp-cooperative gather of encode_imnet's (hoisted) first layer for the warp's 32 queries:
-// lanes 0..15 / 16..31 first compute the two warps' bilinear footprints of 16 queries (thread per
-// query), stage them in the warp's private 2 KB of shared memory, then the whole warp walks the
-// queries one at a time with lane = channel pair, so every tap is one coalesced 128-byte load.
-__device__ __forceinline__ void k2_gather(const K2Params& p, uint8_t* a0, uint4* stg, long tile_q0, int warp_in_wg, int lane,
-                                          float cE0, float cE1) {
+// Warp-cooperative gather of encode_imnet's (hoisted) first layer for the warp's 16 queries.
+// Phase 1: lane = (query, which warp) computes one warp position and its two bilinear footprints
+// (HR grid for Q, LR grid for TE) and stages byte offsets + fp16 weights in the warp's private
+// 1.5 KB of shared memory.  Phase 2: 8 lanes per query, 8 channels per lane: every tap is a
+// 16-byte load (one 128-byte line per query), blended with mixed-precision FMAs (fp16 table value
+// x fp16 weight + fp32 accumulator), then sine -> bf16 -> the SW128 A tile of the first MMA.
+__device__ __forceinline__ void k2_gather(const K2Params& p, uint8_t* a0, uint4* stg, long tile_q0, int warp_in_wg, int lane) {
   const Geometry& g = p.g;
   const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
   const char* __restrict__ tab_b = reinterpret_cast<const char*>(p.tab);
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    {
-      const int qi = lane & 15, which = lane >> 4;
-      const long q = min(tile_q0 + warp_in_wg * 32 + pass * 16 + qi, p.q_end - 1);
-      const int jy = (int)(q / g.WW), jx = (int)(q - (long)jy * g.WW);
-      const float4 fl = __ldg(reinterpret_cast<const float4*>(p.flow) + q);
-      float gy, gx;
-      warp_position(g, jy, jx, which ? fl.z : fl.x, which ? fl.w : fl.y, gy, gx);   // (warplayer.py:25-39)
-      const Taps hr = make_taps(gy, gx, g.HH, g.WW);
-      const Taps lr = make_taps(gy, gx, g.H, g.W);
-      if (p.band_mode) {
+  {
+    const int qi = lane & 15, which = lane >> 4;
+    const long q = min(tile_q0 + warp_in_wg * 16 + qi, p.q_end - 1);
+    const int jy = (int)(q / g.WW), jx = (int)(q - (long)jy * g.WW);
+    const float4 fl = __ldg(reinterpret_cast<const float4*>(p.flow) + q);
+    float gy, gx;
+    warp_position(g, jy, jx, which ? fl.z : fl.x, which ? fl.w : fl.y, gy, gx);   // (warplayer.py:25-39)
+    const Taps hr = make_taps(gy, gx, g.HH, g.WW);
+    const Taps lr = make_taps(gy, gx, g.H, g.W);
+    if (p.band_mode) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (hr.w[k] != 0.f) {
-            const int row = hr.off[k] / g.WW;
-            if (row < p.band_lo || row >= p.band_hi) atomicOr(p.flag, 1);
-          }
-      }
-      uint4 oh, ol, wh, wl;
-      oh.x = (uint32_t)hr.off[0] * 256u + which * 128u; oh.y = (uint32_t)hr.off[1] * 256u + which * 128u;
-      oh.z = (uint32_t)hr.off[2] * 256u + which * 128u; oh.w = (uint32_t)hr.off[3] * 256u + which * 128u;
-      ol.x = (uint32_t)lr.off[0] * 512u + 256u + which * 128u; ol.y = (uint32_t)lr.off[1] * 512u + 256u + which * 128u;
-      ol.z = (uint32_t)lr.off[2] * 512u + 256u + which * 128u; ol.w = (uint32_t)lr.off[3] * 512u + 256u + which * 128u;
-      wh = make_uint4(__float_as_uint(hr.w[0]), __float_as_uint(hr.w[1]), __float_as_uint(hr.w[2]), __float_as_uint(hr.w[3]));
-      wl = make_uint4(__float_as_uint(lr.w[0]), __float_as_uint(lr.w[1]), __float_as_uint(lr.w[2]), __float_as_uint(lr.w[3]));
-      uint4* dst = stg + qi * 8 + which * 4;
-      dst[0] = oh; dst[1] = ol; dst[2] = wh; dst[3] = wl;
-    }
-    __syncwarp();
-#pragma unroll 4
-    for (int i = 0; i < 16; ++i) {
-      const uint4* sq = stg + i * 8;
-      float acc0 = cE0, acc1 = cE1;
-#pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const uint4 oh = sq[which * 4 + 0], ol = sq[which * 4 + 1], wh = sq[which * 4 + 2], wl = sq[which * 4 + 3];
-        const uint32_t o_h[4] = {oh.x, oh.y, oh.z, oh.w}, o_l[4] = {ol.x, ol.y, ol.z, ol.w};
-        const uint32_t w_h[4] = {wh.x, wh.y, wh.z, wh.w}, w_l[4] = {wl.x, wl.y, wl.z, wl.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack_half2(__ldg(reinterpret_cast<const uint32_t*>(qtab_b + o_h[k]) + lane));
-          const float w = __uint_as_float(w_h[k]);
-          acc0 = fmaf(w, f.x, acc0);
-          acc1 = fmaf(w, f.y, acc1);
+      for (int k = 0; k < 4; ++k)
+        if (hr.w[k] != 0.f) {
+          const int row = hr.off[k] / g.WW;
+          if (row < p.band_lo || row >= p.band_hi) atomicOr(p.flag, 1);
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = unpack_half2(__ldg(reinterpret_cast<const uint32_t*>(tab_b + o_l[k]) + lane));
-          const float w = __uint_as_float(w_l[k]);
-          acc0 = fmaf(w, f.x, acc0);
-          acc1 = fmaf(w, f.y, acc1);
-        }
-      }
-      const int r = warp_in_wg * 32 + pass * 16 + i;
-      *reinterpret_cast<uint32_t*>(a0 + sw128_offset(r, 2 * lane)) = pack_bf16x2(fast_sin(acc0), fast_sin(acc1));
     }
-    __syncwarp();
+    const uint32_t cb = which * 128u;
+    uint4* dst = stg + qi * 6;
+    dst[which * 2 + 0] = make_uint4((uint32_t)hr.off[0] * 256u + cb, (uint32_t)hr.off[1] * 256u + cb,
+                                    (uint32_t)hr.off[2] * 256u + cb, (uint32_t)hr.off[3] * 256u + cb);
+    dst[which * 2 + 1] = make_uint4((uint32_t)lr.off[0] * 512u + 256u + cb, (uint32_t)lr.off[1] * 512u + 256u + cb,
+                                    (uint32_t)lr.off[2] * 512u + 256u + cb, (uint32_t)lr.off[3] * 512u + 256u + cb);
+    dst[4 + which] = make_uint4(pack_half2(hr.w[0], hr.w[1]), pack_half2(hr.w[2], hr.w[3]), pack_half2(lr.w[0], lr.w[1]),
+                                pack_half2(lr.w[2], lr.w[3]));
   }
+  __syncwarp();
+  const int sub = lane & 7;
+  float cE[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) cE[e] = p.c.cE[sub * 8 + e];
+#pragma unroll 1
+  for (int it = 0; it < 4; ++it) {
+    const int qloc = it * 4 + (lane >> 3);
+    const uint4* sq = stg + qloc * 6;
+    const uint4 o0 = sq[0], o1 = sq[1], o2 = sq[2], o3 = sq[3], wA = sq[4], wB = sq[5];
+    const uint32_t off[16] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x, o2.y, o2.z, o2.w, o3.x, o3.y, o3.z, o3.w};
+    const uint32_t wpk[8] = {wA.x, wA.y, wA.z, wA.w, wB.x, wB.y, wB.z, wB.w};
+    uint4 v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const char* base = ((k >> 2) & 1) ? tab_b : qtab_b;
+      v[k] = __ldg(reinterpret_cast<const uint4*>(base + off[k]) + sub);
+    }
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = cE[e];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const uint16_t w = (uint16_t)((k & 1) ? (wpk[k >> 1] >> 16) : (wpk[k >> 1] & 0xFFFF));
+      const uint32_t w4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] = fma_f16((uint16_t)(w4[e] & 0xFFFF), w, acc[2 * e]);
+        acc[2 * e + 1] = fma_f16((uint16_t)(w4[e] >> 16), w, acc[2 * e + 1]);
+      }
+    }
+    const int r = warp_in_wg * 16 + qloc;
+    *reinterpret_cast<uint4*>(a0 + sw128_offset(r, sub * 8)) =
+        make_uint4(pack_bf16x2(fast_sin(acc[0]), fast_sin(acc[1])), pack_bf16x2(fast_sin(acc[2]), fast_sin(acc[3])),
+                   pack_bf16x2(fast_sin(acc[4]), fast_sin(acc[5])), pack_bf16x2(fast_sin(acc[6]), fast_sin(acc[7])));
+  }
+  __syncwarp();
 }
 
-__global__ void __launch_bounds__(256, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  const CtaSetup s = cta_prologue(smem_raw, k2Bars, p.wimg, k2WBytes);
-  WgCtx cx = make_wg(s);
-  const uint32_t wsm = smem_u32(s.smem);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warp_in_wg = warp & 3;
-  uint8_t* a0 = s.smem + k2A0 + cx.wg * 16384;
-  uint4* stg = reinterpret_cast<uint4*>(s.smem + k2Taps + warp * 2048);
-  const float cE0 = p.c.cE[2 * lane], cE1 = p.c.cE[2 * lane + 1];
+template <int CH>
+__device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
+  const uint32_t wsm = smem_u32(smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warp_in_wg = warp & 7;
+  uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
+  uint4* stg = reinterpret_cast<uint4*>(smem + k2Taps + warp * 1536);
+  float4* part = reinterpret_cast<float4*>(smem + k2Taps + cx.wg * 8 * 1536);   // reuses the WG's tap staging
   const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
+  constexpr int ch0 = CH * 32;
 
   for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
     const long tile_q0 = p.q_begin + tile * kTile;
-    const long q = tile_q0 + cx.tid_wg;
+    const long q = tile_q0 + cx.row;
     const bool valid = q < p.q_end;
 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
-    k2_gather(p, a0, stg, tile_q0, warp_in_wg, lane, cE0, cE1);
+    k2_gather(p, a0, stg, tile_q0, warp_in_wg, lane);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_barrier(cx.wg);
 
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
     run_layer<1>(cx, smem_u32(a0), 0, wsm + k2E1, 64, 4, [](int) { return 0; },
-                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin, p.c.e1_b); });
-    run_layer<4>(cx, 0, kColAin, wsm + k2E2, 256, 4, [](int i) { return i; },
-                 [&](int i, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i, p.c.e2_b + 64 * i); });
-    float rgb[3] = {p.c.e4_b[0], p.c.e4_b[1], p.c.e4_b[2]};
+                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0); });
+    run_layer<4>(cx, 0, kColAin, wsm + k2E2, 256, 4, [](int i) { return i; }, [&](int i, uint32_t d) {
+      epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0);
+    });
+    float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4>(cx, 0, kColA, wsm + k2E3, 256, 16, [](int i) { return i; },
-                 [&](int i, uint32_t d) { epi_sin_fma<3>(d, p.c.e3_b + 64 * i, p.c.e4_w + 64 * i, rgb); });
-    if (valid) {
-      p.out[q] = rgb[0];
-      p.out[p.plane + q] = rgb[1];
-      p.out[2 * p.plane + q] = rgb[2];
+                 [&](int i, uint32_t d) { epi_sin_fma<3>(d, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb); });
+    const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
+    if (CH == 1) part[cx.row] = mine;
+    wg_barrier(cx.wg);
+    if (CH == 0 && valid) {
+      const float4 o = part[cx.row];
+      p.out[q] = mine.x + o.x + p.c.e4_b[0];
+      p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
+      p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
     }
+    // the next tile's gather rewrites the staging area `part` aliases: every reader must be done
+    wg_barrier(cx.wg);
   }
-  cta_epilogue(s.tmem_base);
+}
+
+__global__ void __launch_bounds__(512, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
+  const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
+  WgCtx cx = make_wg(s);
+  mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.colhalf == 0) k2_tile_loop<0>(p, s, cx);
+  else k2_tile_loop<1>(p, s, cx);
+  cta_epilogue(s.tmem_base, 512);
 }
 
 void fill_from(float* dst, const std::vector<float>& src, size_t n) { std::copy(src.begin(), src.begin() + n, dst); }
@@ -524,17 +627,23 @@ void fill_from(float* dst, const std::vector<float>& src, size_t n) { std::copy(
 // host side
 // =================================================================================================
 struct TcWeights {
+  uint8_t* d_k0 = nullptr;
   uint8_t* d_k1 = nullptr;
   uint8_t* d_k2 = nullptr;
   K1Consts c1{};
   K2Consts c2{};
   std::vector<float> a_t, a_b, b_t, b_b, e_t, e_b;
-  bool attrs_set = false;
 };
 
 TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   auto* t = new TcWeights();
-  std::vector<uint8_t> i1, i2;
+  std::vector<uint8_t> i0, i1, i2;
+  {
+    std::vector<float> wpad((size_t)256 * 256, 0.f);   // K padded 198 -> 256 with zeros
+    for (int r = 0; r < 256; ++r)
+      for (int k = 0; k < 198; ++k) wpad[(size_t)r * 256 + k] = hw.w_tab[(size_t)r * 198 + k];
+    append_sw128_image(i0, wpad.data(), 256, 256);
+  }
   append_sw128_image(i1, hw.f1_w.data(), 64, 64);
   append_sw128_image(i1, hw.f2_w.data(), 256, 64);
   append_sw128_image(i1, hw.f3_w.data(), 192, 256);
@@ -543,15 +652,18 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   append_sw128_image(i2, hw.e1_w.data(), 64, 64);
   append_sw128_image(i2, hw.e2_w.data(), 256, 64);
   append_sw128_image(i2, hw.e3_w.data(), 256, 256);
-  if (i1.size() != k1WBytes || i2.size() != k2WBytes) {
+  if (i0.size() != k0WBytes || i1.size() != k1WBytes || i2.size() != k2WBytes) {
     err = "internal: weight image size mismatch";
     delete t;
     return nullptr;
   }
-  cudaError_t e = cudaMalloc(&t->d_k1, i1.size());
+  cudaError_t e = cudaMalloc(&t->d_k0, i0.size());
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_k1, i1.size());
   if (e == cudaSuccess) e = cudaMalloc(&t->d_k2, i2.size());
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_k0, i0.data(), i0.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(t->d_k1, i1.data(), i1.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(t->d_k2, i2.data(), i2.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k0_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e != cudaSuccess) {
@@ -579,9 +691,24 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
 
 void tc_weights_destroy(TcWeights* t) {
   if (!t) return;
+  if (t->d_k0) cudaFree(t->d_k0);
   if (t->d_k1) cudaFree(t->d_k1);
   if (t->d_k2) cudaFree(t->d_k2);
   delete t;
+}
+
+cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
+                              int W, void* tab) {
+  K0Params p;
+  p.latent = latent192;
+  p.frames = frames6;
+  p.tab = reinterpret_cast<__half*>(tab);
+  p.wimg = tw->d_k0;
+  p.HW = (long)H * W;
+  const long ntiles = (p.HW + kTile - 1) / kTile;
+  k0_project_kernel<<<(int)std::min<long>(cx.num_sms, ntiles), 256, k0Smem, cx.stream>>>(p);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
 }
 
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
@@ -603,7 +730,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.q_end = k1_row_end * WW;
     const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
     const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
-    k1_stage_ab_kernel<<<grid, 256, k1Smem, cx.stream>>>(p);
+    k1_stage_ab_kernel<<<grid, 512, k1Smem, cx.stream>>>(p);
     ++*cx.launch_counter;
     return cudaGetLastError();
   }
@@ -625,7 +752,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.flag = ws.flag;
   const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
-  k2_stage_cde_kernel<<<grid, 256, k2Smem, cx.stream>>>(p);
+  k2_stage_cde_kernel<<<grid, 512, k2Smem, cx.stream>>>(p);
   ++*cx.launch_counter;
   return cudaGetLastError();
 }

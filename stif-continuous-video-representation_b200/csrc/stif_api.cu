@@ -200,7 +200,8 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
     const float* fr_b = frames + (size_t)b * 6 * H * W;
     {
       ScopedSpan sp(d, stream, 0);
-      CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, prec == STIF_MODE_BF16));
+      if (prec == STIF_MODE_BF16) CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab));
+      else CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false));
     }
     for (int c = 0; c < T; ++c) {
       const float t = times[(size_t)c * B + b];

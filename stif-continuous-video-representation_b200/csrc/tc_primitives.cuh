@@ -155,6 +155,39 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2) and mixed-precision FMA (FHFMA: f16 * f16 + f32)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long r, x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long r, x, y, z;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(z) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+// acc + h * w with h, w fp16 (16-bit operands) and fp32 accumulate
+__device__ __forceinline__ float fma_f16(uint16_t h, uint16_t w, float acc) {
+  float r;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(h), "h"(w), "f"(acc));
+  return r;
+}
+// acc + h with h fp16
+__device__ __forceinline__ float add_f16(uint16_t h, float acc) {
+  float r;
+  asm("add.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(acc));
+  return r;
+}
+
 // fast sine on the MUFU pipe (abs error ~5e-7 for |x| <~ 100; the result is rounded to bf16 anyway)
 __device__ __forceinline__ float fast_sin(float x) {
   float r;
