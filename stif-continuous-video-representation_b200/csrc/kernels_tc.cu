@@ -24,6 +24,7 @@
 // overlaps the sine epilogue of chunk c; the other WG's tile fills the remaining bubbles).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,7 @@ namespace {
 using namespace tc;
 
 constexpr int kTile = 128;
+constexpr int kDephaseK1 = 0, kDephaseK2 = 0;   // default WG1 start offsets (clocks); see dephase_clocks()
 constexpr uint32_t kColA = 0;     // A-area: 256-wide activations, channel k at column k/2
 constexpr uint32_t kColAin = 96;  // 64-wide activations live in the last 32 columns of the A-area
 constexpr uint32_t kColD = 128;   // two accumulator slots: [128,192), [192,256)
@@ -77,6 +79,8 @@ struct K1Params {
   float* flow;         // [HH*WW,4]
   const uint8_t* wimg;
   long q_begin, q_end;
+  long long* trace;    // debug: clock64 timestamps of block 0 (STIF_TRACE=<file>), else null
+  int dephase_clk;     // WG1 starts this many clocks after WG0 so the two tiles' phases interleave
 };
 struct K2Params {
   K2Consts c;
@@ -90,6 +94,8 @@ struct K2Params {
   long q_begin, q_end;
   int band_lo, band_hi, band_mode;
   int* flag;
+  long long* trace;
+  int dephase_clk;
 };
 struct K0Params {
   const float* latent;  // [192, HW]
@@ -97,6 +103,7 @@ struct K0Params {
   __half* tab;          // [HW, 256]
   const uint8_t* wimg;  // W_tab, bf16, [256 x 256 (K padded)] SW128 image
   long HW;
+  long m_begin, m_end;  // texel range of this launch (row bands let the host pipeline H2D copies with K0)
 };
 
 extern __shared__ __align__(1024) uint8_t smem[];
@@ -107,8 +114,18 @@ struct WgCtx {
   uint32_t lane_addr;  // same + this warp's lane quarter (for tcgen05.ld/st)
   uint64_t* full;      // two mbarriers: accumulator slot s is complete
   uint32_t n_issued, n_waited;
-  int wg, tid_wg, row, colhalf;
+  int wg, tid_wg, warp_in_wg, row, colhalf;
+  long long* trace;    // this thread's trace cursor (null unless tracing)
 };
+
+// debug timeline: one (tag, clock) pair per call, only for the traced threads of block 0
+__device__ __forceinline__ void trace_mark(WgCtx& cx, int tag) {
+  if (cx.trace) {
+    cx.trace[0] = tag;
+    cx.trace[1] = clock64();
+    cx.trace += 2;
+  }
+}
 
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
 
@@ -124,20 +141,36 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
   }
 }
 
-// Issue the MMAs of one 64-wide output chunk (thread 0 of the WG only) and commit to the slot's barrier.
-//   a_smem != 0: A operand is an SW128 tile in shared memory (K = 64); else A is in TMEM at column a_col.
-__device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_smem, uint32_t a_col, uint32_t w_smem, int n_rows,
-                                            int chunk, int ksteps) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
+  return p != 0;
+}
+
+// Issue the MMAs of one 64-wide output chunk and commit to the slot's barrier.  Executed by warp 0 of
+// the WG with warp-uniform operands (one elected lane issues), so the descriptors live in uniform
+// registers and each tcgen05.mma costs a couple of instructions.
+//   A_SMEM: A operand is an SW128 tile in shared memory at a_base (K = 64); else A is in TMEM at address a_base.
+template <int KSTEPS, bool A_SMEM>
+__device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, int chunk) {
   const uint32_t slot = cx.n_issued & 1;
-  if (cx.tid_wg == 0) {
+  if (cx.warp_in_wg == 0) {
+    tc_fence_after();
     const uint32_t idesc = make_idesc_bf16(128, 64);
     const uint32_t d = cx.tmem + kColD + slot * 64;
-    for (int j = 0; j < ksteps; ++j) {
-      const uint64_t bdesc = make_desc_sw128(w_smem + (uint32_t)(j >> 2) * (uint32_t)n_rows * 128u + (uint32_t)chunk * 8192u) + 2 * (j & 3);
-      if (a_smem) umma_ss(d, make_desc_sw128(a_smem) + 2 * j, bdesc, idesc, j > 0);
-      else umma_ts(d, cx.tmem + a_col + 8 * j, bdesc, idesc, j > 0);
+    const uint64_t b0 = make_desc_sw128(w_smem + (uint32_t)chunk * 8192u);
+    const uint64_t kb = (uint64_t)(((uint32_t)n_rows * 128u) >> 4);   // K-block stride in descriptor units
+    const uint64_t a0 = A_SMEM ? make_desc_sw128(a_base) : 0;
+    if (elect_one()) {
+#pragma unroll
+      for (int j = 0; j < KSTEPS; ++j) {
+        const uint64_t bdesc = b0 + (uint64_t)(j >> 2) * kb + 2 * (j & 3);
+        if (A_SMEM) umma_ss(d, a0 + 2 * j, bdesc, idesc, j > 0);
+        else umma_ts(d, a_base + 8 * j, bdesc, idesc, j > 0);
+      }
+      umma_commit(&cx.full[slot]);
     }
-    umma_commit(&cx.full[slot]);
+    __syncwarp();
   }
   ++cx.n_issued;
 }
@@ -152,26 +185,37 @@ __device__ __forceinline__ uint32_t wait_chunk(WgCtx& cx) {
   return cx.lane_addr + kColD + slot * 64 + cx.colhalf * 32;
 }
 
-// One MLP layer: NC output chunks of 64.  Preconditions: the A operand is complete and a WG barrier
-// has been passed since it was written and since both accumulator slots were last read.
-template <int NC, class ChunkOf, class Epi>
-__device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_smem, uint32_t a_col, uint32_t w_smem, int n_rows, int ksteps,
-                                          ChunkOf chunk_of, Epi epi) {
-  if (cx.tid_wg == 0) tc_fence_after();
-  issue_chunk(cx, a_smem, a_col, w_smem, n_rows, chunk_of(0), ksteps);
-  if (NC > 1) issue_chunk(cx, a_smem, a_col, w_smem, n_rows, chunk_of(1), ksteps);
+// One MLP layer = NC output chunks of 64, in two halves so that independent work (a gather) can be
+// placed between the first MMA issue and the first wait.
+// Preconditions of layer_begin: the A operand is complete and a WG barrier has been passed since it
+// was written and since both accumulator slots were last read.
+template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf>
+__device__ __forceinline__ void layer_begin(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of) {
+  issue_chunk<KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of(0));
+  if (NC > 1) issue_chunk<KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of(1));
+}
+template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf, class Epi>
+__device__ __forceinline__ void layer_finish(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
     const uint32_t d = wait_chunk(cx);
+    trace_mark(cx, 10 + i);
     epi(i, d);
+    trace_mark(cx, 20 + i);
     tc_fence_before();
     wg_barrier(cx.wg);
-    if (i + 2 < NC) {
-      if (cx.tid_wg == 0) tc_fence_after();
-      issue_chunk(cx, a_smem, a_col, w_smem, n_rows, chunk_of(i + 2), ksteps);
-    }
+    trace_mark(cx, 30 + i);
+    if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));
   }
 }
+template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf, class Epi>
+__device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
+  layer_begin<NC, KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of);
+  layer_finish<NC, KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of, epi);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ float2 ldc2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
@@ -291,16 +335,20 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem_base, uint32_t tmem_c
 __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   WgCtx cx;
   const int tid = threadIdx.x;
-  cx.wg = tid >> 8;
+  // warp-uniform quantities are broadcast from lane 0 so that ptxas keeps them in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  cx.wg = warp >> 3;
   cx.tid_wg = tid & 255;
-  const int warp_in_wg = cx.tid_wg >> 5;
+  const int warp_in_wg = warp & 7;
+  cx.warp_in_wg = warp_in_wg;
   const int quarter = warp_in_wg & 3;        // == (global warp id) % 4 : the TMEM lane quarter this warp may access
   cx.colhalf = warp_in_wg >> 2;
   cx.row = quarter * 32 + (tid & 31);
-  cx.tmem = s.tmem_base + (uint32_t)cx.wg * 256u;
+  cx.tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0) + (uint32_t)cx.wg * 256u;
   cx.lane_addr = cx.tmem + ((uint32_t)(quarter * 32) << 16);
   cx.full = s.bars + 1 + 2 * cx.wg;
   cx.n_issued = cx.n_waited = 0;
+  cx.trace = nullptr;
   return cx;
 }
 
@@ -311,14 +359,14 @@ __global__ void __launch_bounds__(256, 1) k0_project_kernel(const __grid_constan
   const CtaSetup s = cta_prologue(k0Bars, k0B, p.wimg, k0WBytes, 256);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row = tid & 127, khalf = tid >> 7;
-  const long ntiles = (p.HW + kTile - 1) / kTile;
+  const long ntiles = (p.m_end - p.m_begin + kTile - 1) / kTile;
   const uint32_t a_sm = smem_u32(smem + k0A), b_sm = smem_u32(smem + k0B);
   // K index 200..207 (group 25) is padding: zero it once (B is zero there too, but 0 * garbage could be NaN)
   if (khalf == 1) *reinterpret_cast<uint4*>(smem + k0A + 3 * 16384 + sw128_offset(row, 8)) = make_uint4(0, 0, 0, 0);
   mbar_wait_or_trap(&s.bars[0], 0);
   uint32_t phase = 0;
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long m = min(tile * kTile + row, p.HW - 1);
+    const long m = min(p.m_begin + tile * kTile + row, p.m_end - 1);
     // ---- A tile: thread = (texel row, half of the channel groups); 8 channels -> one 16-byte smem chunk
 #pragma unroll 1
     for (int gg = 0; gg < 13; ++gg) {
@@ -353,14 +401,14 @@ __global__ void __launch_bounds__(256, 1) k0_project_kernel(const __grid_constan
     // ---- epilogue: warp = (lane quarter, column half); thread = one texel row, 128 channels
     {
       const int quarter = warp & 3, colhalf = warp >> 2;
-      const long texel = tile * kTile + quarter * 32 + lane;
+      const long texel = p.m_begin + tile * kTile + quarter * 32 + lane;
       const uint32_t src = s.tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(src + c * 32, v);
         tmem_ld_wait();
-        if (texel < p.HW) {
+        if (texel < p.m_end) {
           uint4* dst = reinterpret_cast<uint4*>(p.tab + texel * 256 + colhalf * 128 + c * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -392,10 +440,17 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
   constexpr int ch0 = CH * 32;   // this thread's 32 channels of every 64-wide vector
 
   for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
+    if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;   // trace the first 16 tiles only
     const long q = p.q_begin + tile * kTile + cx.row;
     const bool valid = q < p.q_end;
     const long qc = valid ? q : p.q_end - 1;
     const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
+    trace_mark(cx, 1);
+    {  // stage-B tap lines of this tile -> L1 now; they are consumed ~15k clocks later
+      const Taps tp = make_taps_tables(g, jy, jx);
+      prefetch_l1(tab4 + (long)tp.off[2 * CH] * 32 + 8);
+      prefetch_l1(tab4 + (long)tp.off[2 * CH + 1] * 32 + 8);
+    }
 
     // ---- stage A, first layer (hoisted): h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
     {
@@ -420,17 +475,22 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
       tmem_st_wait();
     }
+    trace_mark(cx, 2);
     tc_fence_before();
     wg_barrier(cx.wg);
+    trace_mark(cx, 3);
 
     // ---- feat_imnet hidden layers
-    run_layer<1>(cx, 0, kColAin, wsm + k1F1, 64, 4, [](int) { return 0; },
+    run_layer<1, 4, false>(cx, cx.tmem + kColAin, wsm + k1F1, 64, [](int) { return 0; },
                  [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0); });
-    run_layer<4>(cx, 0, kColAin, wsm + k1F2, 256, 4, [](int i) { return i; }, [&](int i, uint32_t d) {
+    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t d) {
       epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0);
     });
 
-    // ---- stage B gather, issued before the composed layer so its latency hides behind the MMAs:
+    // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
+    auto f3_order = [](int i) { return i == 2 ? 0 : i + 1; };
+    layer_begin<3, 16, false>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order);
+    // ---- stage B gather, placed after the composed layer's first MMAs are issued so its latency hides behind them:
     //      gB = bilinear(TB; query position) + cB + composed bias of F                  (:410-418)
     float gB[32];
     {
@@ -455,17 +515,17 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       }
     }
 
-    // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
-    run_layer<3>(cx, 0, kColA, wsm + k1F3, 192, 16, [](int i) { return i == 2 ? 0 : i + 1; }, [&](int i, uint32_t d) {
+    trace_mark(cx, 4);
+    layer_finish<3, 16, false>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t d) {
       if (i < 2) epi_store_qtab(d, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid);
       else epi_flow_first_layer(d, cx.lane_addr + kColAin + CH * 16, gB);
     });
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
-    run_layer<1>(cx, 0, kColAin, wsm + k1L1, 64, 4, [](int) { return 0; },
+    run_layer<1, 4, false>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
                  [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0); });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4>(cx, 0, kColAin, wsm + k1L2, 256, 4, [](int i) { return i; },
+    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
                  [&](int i, uint32_t d) { epi_sin_fma<4>(d, p.c.l2_b + 64 * i + ch0, p.c.l3_w + 64 * i + ch0, fl); });
     // combine the two column halves and store
     const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
@@ -482,7 +542,12 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
 __global__ void __launch_bounds__(512, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
   const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
   WgCtx cx = make_wg(s);
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.wg == 1 && p.dephase_clk > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.dephase_clk) __nanosleep(200);
+  }
   if (cx.colhalf == 0) k1_tile_loop<0>(p, s, cx);
   else k1_tile_loop<1>(p, s, cx);
   cta_epilogue(s.tmem_base, 512);
@@ -577,24 +642,40 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   constexpr int ch0 = CH * 32;
 
   for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
+    if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
     const long tile_q0 = p.q_begin + tile * kTile;
     const long q = tile_q0 + cx.row;
     const bool valid = q < p.q_end;
 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
+    trace_mark(cx, 1);
+    {  // L2 prefetch for this WG's NEXT tile: the lines a small flow would touch (own pixel, rows -1/0/+1).
+       // Pure hint: a wrong guess costs nothing but the prefetch itself.
+      const long qn = tile_q0 + (long)gridDim.x * 2 * kTile + cx.row;
+      if (qn < p.q_end) {
+        const char* base = reinterpret_cast<const char*>(p.qtab) + CH * 128;
+        const long W2 = (long)p.g.WW;
+        prefetch_l2(base + qn * 256);
+        if (qn >= W2) prefetch_l2(base + (qn - W2) * 256);
+        if (qn + W2 < p.plane) prefetch_l2(base + (qn + W2) * 256);
+        if (CH == 0) prefetch_l2(reinterpret_cast<const float4*>(p.flow) + qn);
+      }
+    }
     k2_gather(p, a0, stg, tile_q0, warp_in_wg, lane);
+    trace_mark(cx, 2);
     fence_proxy_async_smem();
     tc_fence_before();
     wg_barrier(cx.wg);
+    trace_mark(cx, 3);
 
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
-    run_layer<1>(cx, smem_u32(a0), 0, wsm + k2E1, 64, 4, [](int) { return 0; },
+    run_layer<1, 4, true>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
                  [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0); });
-    run_layer<4>(cx, 0, kColAin, wsm + k2E2, 256, 4, [](int i) { return i; }, [&](int i, uint32_t d) {
+    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t d) {
       epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4>(cx, 0, kColA, wsm + k2E3, 256, 16, [](int i) { return i; },
+    run_layer<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
                  [&](int i, uint32_t d) { epi_sin_fma<3>(d, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb); });
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
@@ -613,7 +694,12 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
 __global__ void __launch_bounds__(512, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
   WgCtx cx = make_wg(s);
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.wg == 1 && p.dephase_clk > 0) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < p.dephase_clk) __nanosleep(200);
+  }
   if (cx.colhalf == 0) k2_tile_loop<0>(p, s, cx);
   else k2_tile_loop<1>(p, s, cx);
   cta_epilogue(s.tmem_base, 512);
@@ -698,18 +784,59 @@ void tc_weights_destroy(TcWeights* t) {
 }
 
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
-                              int W, void* tab) {
+                              int W, void* tab, int row_begin, int row_end) {
   K0Params p;
   p.latent = latent192;
   p.frames = frames6;
   p.tab = reinterpret_cast<__half*>(tab);
   p.wimg = tw->d_k0;
   p.HW = (long)H * W;
-  const long ntiles = (p.HW + kTile - 1) / kTile;
+  p.m_begin = (long)row_begin * W;
+  p.m_end = (long)row_end * W;
+  const long ntiles = (p.m_end - p.m_begin + kTile - 1) / kTile;
   k0_project_kernel<<<(int)std::min<long>(cx.num_sms, ntiles), 256, k0Smem, cx.stream>>>(p);
   ++*cx.launch_counter;
   return cudaGetLastError();
 }
+
+namespace {
+// STIF_TRACE=<path>: dump clock64 timelines of block 0 (16 warps x first 16 tiles) for K1 and K2.
+long long* trace_buffer() {
+  static long long* buf = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    if (getenv("STIF_TRACE")) {
+      cudaMalloc(&buf, 16 * 4096 * sizeof(long long));
+    }
+  }
+  return buf;
+}
+// tuning knob (STIF_DEPHASE_K1 / STIF_DEPHASE_K2, clocks)
+int dephase_clocks(int kernel) {
+  static int v[3] = {-1, -1, -1};
+  if (v[kernel] < 0) {
+    const char* e = getenv(kernel == 1 ? "STIF_DEPHASE_K1" : "STIF_DEPHASE_K2");
+    v[kernel] = e ? atoi(e) : (kernel == 1 ? kDephaseK1 : kDephaseK2);
+  }
+  return v[kernel];
+}
+void trace_dump(const char* kernel, cudaStream_t stream) {
+  long long* buf = trace_buffer();
+  if (!buf) return;
+  cudaStreamSynchronize(stream);
+  std::vector<long long> h(16 * 4096);
+  cudaMemcpy(h.data(), buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  FILE* f = fopen(getenv("STIF_TRACE"), "a");
+  if (!f) return;
+  for (int w = 0; w < 16; ++w) {
+    fprintf(f, "%s warp %d:", kernel, w);
+    for (int i = 0; i + 1 < 4096 && h[w * 4096 + i] != 0; i += 2) fprintf(f, " %lld:%lld", h[w * 4096 + i], h[w * 4096 + i + 1]);
+    fprintf(f, "\n");
+  }
+  fclose(f);
+}
+}  // namespace
 
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage) {
@@ -730,8 +857,12 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.q_end = k1_row_end * WW;
     const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
     const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
+    p.trace = trace_buffer();
+    p.dephase_clk = dephase_clocks(1);
+    if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
     k1_stage_ab_kernel<<<grid, 512, k1Smem, cx.stream>>>(p);
     ++*cx.launch_counter;
+    trace_dump("K1", cx.stream);
     return cudaGetLastError();
   }
   K2Params p;
@@ -752,8 +883,12 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.flag = ws.flag;
   const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
+  p.trace = trace_buffer();
+  p.dephase_clk = dephase_clocks(2);
+  if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
   k2_stage_cde_kernel<<<grid, 512, k2Smem, cx.stream>>>(p);
   ++*cx.launch_counter;
+  trace_dump("K2", cx.stream);
   return cudaGetLastError();
 }
 

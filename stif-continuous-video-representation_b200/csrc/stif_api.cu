@@ -67,7 +67,7 @@ struct stif_decoder {
   // stif_decode_host scratch
   void* host_scratch = nullptr;
   size_t host_scratch_bytes = 0;
-  cudaStream_t host_stream = nullptr;
+  cudaStream_t host_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
 };
 
 namespace stif {
@@ -171,9 +171,20 @@ struct ScopedSpan {  // brackets one kernel group with events when profiling is 
   ~ScopedSpan() { if (b) cudaEventRecord(b, s); }
 };
 
+// stif_decode_host: host<->device copies pipelined with the kernels.  The latent is uploaded in row
+// bands on `h2d` (K0 projects each band as soon as it lands) and every finished (t,b) slab is
+// downloaded on `d2h` while the next slab is being decoded.
+struct HostPipe {
+  const float* latent_host;
+  const float* frames_host;
+  float* out_host;
+  cudaStream_t h2d, d2h;
+  int bands;
+};
+
 int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
                 const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
-                size_t workspace_bytes, float* out, cudaStream_t stream, bool check_band) {
+                size_t workspace_bytes, float* out, cudaStream_t stream, bool check_band, const HostPipe* hp = nullptr) {
   if (!d) return set_error(STIF_EINVAL, "null decoder");
   if (!d->weights_loaded) return set_error(STIF_ESTATE, "stif_load_weights has not been called");
   if (!latent || !frames || !times || !out || !workspace) return set_error(STIF_EINVAL, "null buffer");
@@ -195,25 +206,76 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   const int k1_lo = std::max(0, row_begin - halo), k1_hi = std::min(HH, row_end + halo);
   const size_t Q = (size_t)HH * WW;
   CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
+  std::vector<cudaEvent_t> used_events;
+  const int nbands = hp ? std::max(1, std::min(hp->bands, H)) : 1;
+  const size_t plane = (size_t)H * W;
+  // Host pipeline, bf16 mode: stage A+B of the first timestep is launched per row band right behind the
+  // band's projection, so the upload of band k+1 overlaps K0/K1 of band k.  band_hr_end[k] = first HR row
+  // whose nearest / bilinear LR footprint (rows idx, b0, b0+1) is not yet covered by bands 0..k.
+  const bool band_k1 = hp && prec == STIF_MODE_BF16 && nbands > 1 && row_begin == 0 && row_end == HH;
+  std::vector<int> band_hr_end(nbands, HH);
+  if (band_k1) {
+    HostAxis ay;
+    build_axis(H, HH, ay);
+    for (int k = 0; k + 1 < nbands; ++k) {
+      const int r1 = (int)((long)H * (k + 1) / nbands);
+      int h = 0;
+      while (h < HH && ay.idx[h] < r1 && ay.b0[h] + 1 < r1) ++h;
+      band_hr_end[k] = h;
+    }
+  }
   for (int b = 0; b < B; ++b) {
-    const float* lat_b = latent + (size_t)b * 192 * H * W;
-    const float* fr_b = frames + (size_t)b * 6 * H * W;
-    {
+    const float* lat_b = latent + (size_t)b * 192 * plane;
+    const float* fr_b = frames + (size_t)b * 6 * plane;
+    for (int k = 0; k < nbands; ++k) {
+      const int r0 = (int)((long)H * k / nbands), r1 = (int)((long)H * (k + 1) / nbands);
+      if (hp) {   // upload this row band of all 198 channels, then let the compute stream wait for it
+        const size_t off = (size_t)r0 * W, width = (size_t)(r1 - r0) * W * sizeof(float);
+        CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)lat_b + off, plane * 4, hp->latent_host + (size_t)b * 192 * plane + off, plane * 4,
+                                         width, 192, cudaMemcpyHostToDevice, hp->h2d));
+        CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)fr_b + off, plane * 4, hp->frames_host + (size_t)b * 6 * plane + off, plane * 4,
+                                         width, 6, cudaMemcpyHostToDevice, hp->h2d));
+        cudaEvent_t ev = take_event(d);
+        used_events.push_back(ev);
+        CUDA_OR_RETURN(cudaEventRecord(ev, hp->h2d));
+        CUDA_OR_RETURN(cudaStreamWaitEvent(stream, ev, 0));
+      }
       ScopedSpan sp(d, stream, 0);
-      if (prec == STIF_MODE_BF16) CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab));
-      else CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false));
+      if (prec == STIF_MODE_BF16) CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
+      else if (k == nbands - 1) CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false));
+      if (band_k1) {
+        const int h0 = k == 0 ? 0 : band_hr_end[k - 1], h1 = band_hr_end[k];
+        if (h1 > h0) {
+          ScopedSpan sp1(d, stream, 1);
+          cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, ws, times[b], 0, HH, h0, h1, out + (size_t)b * 3 * Q, 1);
+          if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+        }
+      }
     }
     for (int c = 0; c < T; ++c) {
       const float t = times[(size_t)c * B + b];
       float* out_slab = out + ((size_t)c * B + b) * 3 * Q;
-      for (int stage = 1; stage <= 2; ++stage) {
+      for (int stage = (band_k1 && c == 0) ? 2 : 1; stage <= 2; ++stage) {
         ScopedSpan sp(d, stream, stage);
         cudaError_t e = (prec == STIF_MODE_FP32)
                             ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
                             : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
+      if (hp) {   // download this slab while the next one is decoded
+        cudaEvent_t ev = take_event(d);
+        used_events.push_back(ev);
+        CUDA_OR_RETURN(cudaEventRecord(ev, stream));
+        CUDA_OR_RETURN(cudaStreamWaitEvent(hp->d2h, ev, 0));
+        CUDA_OR_RETURN(cudaMemcpyAsync(hp->out_host + ((size_t)c * B + b) * 3 * Q, out_slab, 3 * Q * sizeof(float),
+                                       cudaMemcpyDeviceToHost, hp->d2h));
+      }
     }
+  }
+  if (hp) {
+    CUDA_OR_RETURN(cudaStreamSynchronize(hp->d2h));
+    CUDA_OR_RETURN(cudaStreamSynchronize(stream));
+    for (auto e : used_events) d->event_pool.push_back(e);
   }
   d->last_flow = ws.flow;
   d->last_flow_floats = Q * 4;
@@ -266,6 +328,8 @@ int stif_destroy(stif_decoder_t* d) {
   if (d->tcw) tc_weights_destroy(d->tcw);
   if (d->host_scratch) cudaFree(d->host_scratch);
   if (d->host_stream) cudaStreamDestroy(d->host_stream);
+  if (d->h2d_stream) cudaStreamDestroy(d->h2d_stream);
+  if (d->d2h_stream) cudaStreamDestroy(d->d2h_stream);
   for (auto& sp : d->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto e : d->event_pool) cudaEventDestroy(e);
   delete d;
@@ -330,7 +394,11 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   if (!latent_host || !frames_host || !out_host) return set_error(STIF_EINVAL, "null buffer");
   if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
   CUDA_OR_RETURN(cudaSetDevice(d->device));
-  if (!d->host_stream) CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->host_stream, cudaStreamNonBlocking));
+  if (!d->host_stream) {
+    CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->host_stream, cudaStreamNonBlocking));
+    CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->h2d_stream, cudaStreamNonBlocking));
+    CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
+  }
   const size_t lat_b = align256((size_t)B * 192 * H * W * 4), fr_b = align256((size_t)B * 6 * H * W * 4);
   const size_t out_b = align256((size_t)T * B * 3 * HH * WW * 4);
   const size_t ws_b = stif_workspace_bytes(B, H, W, HH, WW, T, mode);
@@ -348,12 +416,8 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   float* out = (float*)(base + lat_b + fr_b);
   void* ws = base + lat_b + fr_b + out_b;
   cudaStream_t s = d->host_stream;
-  CUDA_OR_RETURN(cudaMemcpyAsync(lat, latent_host, (size_t)B * 192 * H * W * 4, cudaMemcpyHostToDevice, s));
-  CUDA_OR_RETURN(cudaMemcpyAsync(fr, frames_host, (size_t)B * 6 * H * W * 4, cudaMemcpyHostToDevice, s));
-  if (int rc = decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false)) return rc;
-  CUDA_OR_RETURN(cudaMemcpyAsync(out_host, out, (size_t)T * B * 3 * HH * WW * 4, cudaMemcpyDeviceToHost, s));
-  CUDA_OR_RETURN(cudaStreamSynchronize(s));
-  return STIF_OK;
+  HostPipe hp{latent_host, frames_host, out_host, d->h2d_stream, d->d2h_stream, 6};
+  return decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false, &hp);
 }
 
 int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* rel, float* base) {

@@ -86,7 +86,7 @@ void tc_weights_destroy(TcWeights*);
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage);
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
-                              int W, void* tab /* fp16 [H*W,256] */);
+                              int W, void* tab /* fp16 [H*W,256] */, int row_begin, int row_end);
 int tc_selftest(int device, std::string& report);
 
 }  // namespace stif
