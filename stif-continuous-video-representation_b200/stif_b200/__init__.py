@@ -11,3 +11,4 @@ from .decoder import (STIFQueryDecoder, install_class_patch, patch_reference_mod
 
 __all__ = ["STIFQueryDecoder", "patch_reference_model", "install_class_patch", "weight_keys", "axis_tables",
            "selftest", "StifError", "LIB_PATH", "STIF_MODE_BF16", "STIF_MODE_FP32"]
+from .launcher import QueryShardLauncher, WorkUnit, plan_units, units_for_rank  # noqa: E402,F401

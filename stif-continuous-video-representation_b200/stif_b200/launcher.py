@@ -1,0 +1,177 @@
+"""Query-sharding launcher: one process per GPU, (frame-pair, timestep) slabs partitioned across ranks.
+
+The reference decodes on a single device (``custom_video_test.py:2`` pins ``CUDA_VISIBLE_DEVICES=0``)
+and loops over timesteps serially (``Sakuya_arch_test.py:380``); nothing carries between iterations,
+so every (pair, t) slab is an independent unit of work.  This launcher
+
+* broadcasts the decoder weights and the latents / frames ONCE from the encoder rank over the
+  process group (NCCL over NVLink on a B200 box; gloo in the CPU tests),
+* assigns slabs round-robin; when there are fewer slabs than ranks it splits each slab into row
+  bands -- stage A/B of the reference are point-wise (``:382-422``), so a band recomputes its halo rows
+  locally (``stif_decode_rows``) and no data-path exchange is needed,
+* issues NO collective inside the decode loop; an optional gather of the RGB slabs to one rank
+  happens after it.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class WorkUnit:
+    """Rows ``[row_begin, row_end)`` of the output raster of frame pair ``pair`` at time index ``t_index``."""
+    pair: int
+    t_index: int
+    row_begin: int
+    row_end: int
+    rank: int
+
+
+def plan_units(num_pairs: int, num_times: int, HH: int, world: int) -> list[WorkUnit]:
+    """Static partition of the job.  Slabs >= ranks: whole slabs, round-robin.  Otherwise every slab is cut
+    into ``ceil(world / slabs)`` row bands (as even as integer rows allow) and the bands go round-robin."""
+    if min(num_pairs, num_times, HH, world) < 1:
+        raise ValueError("num_pairs, num_times, HH and world must all be >= 1")
+    slabs = [(p, c) for p in range(num_pairs) for c in range(num_times)]
+    units: list[WorkUnit] = []
+    if len(slabs) >= world:
+        for i, (p, c) in enumerate(slabs):
+            units.append(WorkUnit(p, c, 0, HH, i % world))
+        return units
+    bands = min(HH, -(-world // len(slabs)))
+    i = 0
+    for (p, c) in slabs:
+        for k in range(bands):
+            r0, r1 = HH * k // bands, HH * (k + 1) // bands
+            if r1 > r0:
+                units.append(WorkUnit(p, c, r0, r1, i % world))
+                i += 1
+    return units
+
+
+def units_for_rank(units: Sequence[WorkUnit], rank: int) -> list[WorkUnit]:
+    return [u for u in units if u.rank == rank]
+
+
+DecodeFn = Callable[[torch.Tensor, torch.Tensor, float, tuple, tuple | None, int], torch.Tensor]
+
+
+class QueryShardLauncher:
+    """Shards a decode job over the ranks of a ``torch.distributed`` process group.
+
+    ``decode_fn(latent[1,3,64,H,W], frames[1,2,3,H,W], t, (HH,WW), rows|None, halo) -> [3,HH,WW]`` is the
+    per-unit decoder; by default it is a ``STIFQueryDecoder`` on this rank's GPU (rows outside the band
+    are left untouched / zero).  The CPU tests inject a stub so that the host logic runs under gloo."""
+
+    def __init__(self, decode_fn: DecodeFn | None = None, group=None, device: torch.device | str | None = None,
+                 mode: str = "bf16"):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.device(device) if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
+        self._decoder = None
+        self._decode_fn = decode_fn
+        self.mode = mode
+        self.latent: torch.Tensor | None = None
+        self.frames: torch.Tensor | None = None
+
+    # ------------------------------------------------------------------ one-off broadcasts
+    def _bcast(self, t: torch.Tensor | None, shape, src: int) -> torch.Tensor:
+        if self.rank == src:
+            buf = t.to(self.device, torch.float32).contiguous()
+        else:
+            buf = torch.empty(shape, dtype=torch.float32, device=self.device)
+        dist.broadcast(buf, src, group=self.group)
+        return buf
+
+    def broadcast_weights(self, state_dict: dict | None, src: int = 0) -> dict:
+        """0.84 MB: the 26 decoder tensors, flattened into one broadcast."""
+        from .decoder import NET_SHAPES, weight_keys
+        keys = weight_keys()
+        shapes = {}
+        for net, dims in NET_SHAPES.items():
+            n = len(dims) - 1
+            for li in range(n):
+                stem = f"{net}.net.{li}" if li == n - 1 else f"{net}.net.{li}.linear"
+                shapes[f"{stem}.weight"] = (dims[li + 1], dims[li])
+                shapes[f"{stem}.bias"] = (dims[li + 1],)
+        total = sum(int(np.prod(shapes[k])) for k in keys)
+        flat = None
+        if self.rank == src:
+            flat = torch.cat([torch.as_tensor(state_dict[k], dtype=torch.float32).reshape(-1) for k in keys])
+        flat = self._bcast(flat, (total,), src).cpu()
+        out, off = {}, 0
+        for k in keys:
+            n = int(np.prod(shapes[k]))
+            out[k] = flat[off:off + n].reshape(shapes[k]).clone()
+            off += n
+        if self._decode_fn is None:
+            from .decoder import STIFQueryDecoder
+            self._decoder = STIFQueryDecoder(self.device, mode=self.mode)
+            self._decoder.load_weights(out)
+        return out
+
+    def broadcast_inputs(self, latent: torch.Tensor | None, frames: torch.Tensor | None, shape: tuple[int, int, int],
+                         src: int = 0) -> None:
+        """latent ``[P,3,64,H,W]`` and frames ``[P,2,3,H,W]`` from the encoder rank to every rank; ``shape=(P,H,W)``."""
+        P, H, W = shape
+        self.latent = self._bcast(latent, (P, 3, 64, H, W), src)
+        self.frames = self._bcast(frames, (P, 2, 3, H, W), src)
+
+    # ------------------------------------------------------------------ decode loop (no collectives inside)
+    def _decode_unit(self, u: WorkUnit, t: float, out_size, halo: int) -> torch.Tensor:
+        lat, fr = self.latent[u.pair:u.pair + 1], self.frames[u.pair:u.pair + 1]
+        HH = out_size[0]
+        rows = None if (u.row_begin == 0 and u.row_end == HH) else (u.row_begin, u.row_end)
+        if self._decode_fn is not None:
+            return self._decode_fn(lat, fr, t, out_size, rows, halo)
+        from ._lib import StifError
+        h = halo
+        while True:
+            try:
+                out = torch.zeros((1, 1, 3, *out_size), dtype=torch.float32, device=self.device)
+                self._decoder.decode_stacked(lat, fr, [t], out_size, rows=rows, halo=h, out=out)
+                return out[0, 0]
+            except StifError as e:                      # a flow reached outside the halo: widen it and redo the band
+                if "halo" not in str(e) or h >= HH:
+                    raise
+                h = min(HH, max(1, h) * 2)
+
+    def decode(self, times: Sequence[float], out_size: tuple[int, int], halo: int = 32):
+        """Decode this rank's share.  Returns ``[(WorkUnit, tensor[3,HH,WW])]``; for band units only rows
+        ``[row_begin,row_end)`` of the tensor are meaningful."""
+        if self.latent is None:
+            raise RuntimeError("broadcast_inputs() first")
+        P = self.latent.shape[0]
+        units = plan_units(P, len(times), out_size[0], self.world)
+        return [(u, self._decode_unit(u, float(times[u.t_index]), tuple(out_size), halo))
+                for u in units_for_rank(units, self.rank)]
+
+    # ------------------------------------------------------------------ optional result collection
+    def gather(self, results, times, out_size, dst: int = 0) -> torch.Tensor | None:
+        """Assemble ``[T,P,3,HH,WW]`` on rank ``dst`` (after the decode loop; row bands are stitched)."""
+        P, T = self.latent.shape[0], len(times)
+        HH, WW = out_size
+        units = plan_units(P, T, HH, self.world)
+        full = torch.zeros((T, P, 3, HH, WW), dtype=torch.float32, device=self.device) if self.rank == dst else None
+        mine = {(u.pair, u.t_index, u.row_begin): t for u, t in results}
+        for u in units:
+            band = (3, u.row_end - u.row_begin, WW)
+            if u.rank == dst:
+                if self.rank == dst:
+                    full[u.t_index, u.pair, :, u.row_begin:u.row_end] = mine[(u.pair, u.t_index, u.row_begin)][:, u.row_begin:u.row_end]
+            elif self.rank == u.rank:
+                dist.send(mine[(u.pair, u.t_index, u.row_begin)][:, u.row_begin:u.row_end].contiguous(), dst, group=self.group)
+            elif self.rank == dst:
+                buf = torch.empty(band, dtype=torch.float32, device=self.device)
+                dist.recv(buf, u.rank, group=self.group)
+                full[u.t_index, u.pair, :, u.row_begin:u.row_end] = buf
+        return full
