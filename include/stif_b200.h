@@ -92,8 +92,8 @@ size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode
  *   (HH,WW)     output raster size; the reference's `scale` argument IS this size
  *               (Sakuya_arch_test.py:368-371); the x4 default is (4H,4W)
  *   out_rgb_dev [T,B,3,HH,WW] fp32, unclamped (== torch.stack(preds))
- * With STIF_FLAG_LOCAL_ENSEMBLE the result is decoding_localensemble's (B must be 1 there, as in the
- * reference, and out is [T,3,HH,WW]). */
+ * With STIF_FLAG_LOCAL_ENSEMBLE (STIF_MODE_FP32 only in this build) the result is
+ * decoding_localensemble's: B must be 1 as in the reference, out is [T,1,3,HH,WW]. */
 int stif_decode(stif_decoder_t* dec,
                 const float* latent_dev, const float* frames_dev,
                 int B, int H, int W, int HH, int WW,
@@ -133,6 +133,12 @@ int stif_decode_host(stif_decoder_t* dec,
  *   rel    (coord - lr_coord[index]) * n_lr         (:394-396)         -- bit-exact contract
  *   base   warp base grid, linspace(-1,1,n_hr)      (warplayer.py:28-31) */
 int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* rel, float* base);
+
+/* Blend weights of decoding_localensemble (Sakuya_arch_test.py:1011-1012, 1077-1084), HOST output
+ * [4, HH*WW]: weights[k*HH*WW + q] = area_{3-k}[q] / tot_area[q] multiplies pass k's prediction
+ * (pass order (vx,vy) = (-1,-1), (-1,1), (1,-1), (1,1)).  Bit-exact contract; the decode kernels
+ * recompute the same value with IEEE-rounded intrinsics. */
+int stif_ensemble_weights(int H, int W, int HH, int WW, float* weights_host, size_t num_floats);
 
 /* Copy stage intermediates of the LAST slab decoded by `dec` to HOST buffers (any may be NULL):
  *   flow [HH*WW,4] fp32 -- flow_imnet output (dx1,dy1,dx2,dy2), HR-pixel units (:419-422).

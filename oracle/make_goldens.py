@@ -97,7 +97,26 @@ def run_case(name: str, cfg: dict) -> dict:
             clear_warp_cache()
             fast = model.decoding_fasttest(tl, cfg["scale"])
             clear_warp_cache()
-            ens = model.decoding_localensemble(tl, cfg["scale"])
+            # the blend weights are locals of the reference method: capture them at its return
+            # (post-swap `areas` and `tot_area`, Sakuya_arch_test.py:1078-1084)
+            grabbed = {}
+
+            def tracer(frame, event, arg):
+                if frame.f_code.co_name != "decoding_localensemble":
+                    return None
+
+                def local(frame, event, arg):
+                    if event == "return":
+                        grabbed["areas"] = [a.numpy().copy() for a in frame.f_locals["areas"]]
+                        grabbed["tot"] = frame.f_locals["tot_area"].numpy().copy()
+                    return local
+                return local
+            sys.settrace(tracer)
+            try:
+                ens = model.decoding_localensemble(tl, cfg["scale"])
+            finally:
+                sys.settrace(None)
+            out["ensemble_weights"] = np.stack([(a / grabbed["tot"])[0] for a in grabbed["areas"]], 0).astype(np.float32)
         out["rgb_fasttest"] = fast.numpy().astype(np.float32)
         out["rgb_localensemble"] = ens.numpy().astype(np.float32)
     return out

@@ -222,6 +222,83 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
     return (out, stages) if return_stages else out
 
 
+# ----------------------------------------------------------------------------- local ensemble
+ENSEMBLE_SHIFTS = [(-1, -1), (-1, 1), (1, -1), (1, 1)]      # (vx, vy) loop order, Sakuya_arch_test.py:978-988
+EPS_SHIFT = 1e-6
+
+
+def shifted_axis_tables(n_lr: int, n_hr: int, v: int) -> dict:
+    """Per-axis tables of ``decoding_localensemble`` for shift sign ``v`` (``:981-995``): the query coordinate is
+    moved by ``v * (1/n_lr) + 1e-6`` (python double -> fp32 at the in-place add) and re-clamped; EVERY gather uses
+    the shifted coordinate, but ``rel`` is taken from the un-shifted one (``:1008``)."""
+    c = clamp_axis(make_axis(n_hr))
+    cs = clamp_axis((c + F32(v * (2.0 / n_lr / 2.0) + EPS_SHIFT)).astype(F32))
+    lr_c = make_axis(n_lr)
+    i = nearest_index(cs, n_lr)
+    inb = (i >= 0) & (i < n_lr)
+    q = np.where(inb, lr_c[np.clip(i, 0, n_lr - 1)], F32(0.0)).astype(F32)
+    rel = ((c - q) * F32(n_lr)).astype(F32)
+    return {"c": c, "cs": cs, "i": i, "rel": rel, "hi": nearest_index(cs, n_hr), "base": linspace_axis(n_hr)}
+
+
+def ensemble_weights(H: int, W: int, HH: int, WW: int) -> np.ndarray:
+    """``area_k / tot_area`` AFTER the 0<->3, 1<->2 swap (``:1079-1084``), shape ``[4, HH*WW]`` -- the weight that
+    multiplies pass k's prediction.  fp32, separately rounded: area = abs(rel_y * rel_x) + fl32(1e-9)."""
+    jy, jx = np.divmod(np.arange(HH * WW), WW)
+    areas = []
+    for vx, vy in ENSEMBLE_SHIFTS:
+        ry = shifted_axis_tables(H, HH, vx)["rel"][jy]
+        rx = shifted_axis_tables(W, WW, vy)["rel"][jx]
+        areas.append((np.abs((ry * rx).astype(F32)) + F32(1e-9)).astype(F32))
+    tot = (((areas[0] + areas[1]).astype(F32) + areas[2]).astype(F32) + areas[3]).astype(F32)
+    return np.stack([(areas[3 - k] / tot).astype(F32) for k in range(4)], 0)
+
+
+def decode_localensemble(latent, frames, weights, times, scale=None):
+    """Restatement of ``LunaTokis.decoding_localensemble`` (``:962-1085``; batch size 1 as in the reference).
+    Returns ``[T,3,HH,WW]``."""
+    latent = np.asarray(latent, dtype=F32)
+    frames = np.asarray(frames, dtype=F32)
+    assert latent.shape[0] == 1
+    _, _, _, H, W = latent.shape
+    HH, WW = (4 * H, 4 * W) if scale is None else (int(scale[0]), int(scale[1]))
+    feat, fr = latent[0].reshape(192, H, W), frames[0].reshape(6, H, W)
+    Q = HH * WW
+    jy, jx = np.divmod(np.arange(Q), WW)
+    wts = ensemble_weights(H, W, HH, WW)
+    out = np.zeros((len(times), 3, HH, WW), dtype=F32)
+    for c, t in enumerate(times):
+        t = F32(t)
+        ret = np.zeros((Q, 3), dtype=F32)
+        for k, (vx, vy) in enumerate(ENSEMBLE_SHIFTS):
+            ay, ax = shifted_axis_tables(H, HH, vx), shifted_axis_tables(W, WW, vy)
+            iy, ix = ay["i"][jy], ax["i"][jx]
+            ok = ((iy >= 0) & (iy < H) & (ix >= 0) & (ix < W)).astype(F32)[:, None]
+            iyc, ixc = np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)
+            a_in = np.concatenate([feat[:, iyc, ixc].T * ok, fr[:, iyc, ixc].T * ok, ay["rel"][jy][:, None],
+                                   ax["rel"][jx][:, None], np.full((Q, 1), t, dtype=F32)], 1).astype(F32)
+            hr = siren(a_in, weights, "feat_imnet")
+            hr_map = np.ascontiguousarray(hr.T).reshape(64, HH, WW)
+            ys, xs = ay["cs"][jy], ax["cs"][jx]
+            b_in = np.concatenate([gather_nearest(hr_map, ys, xs), gather_bilinear(feat, ys, xs),
+                                   gather_bilinear(fr, ys, xs), np.full((Q, 1), t, dtype=F32)], 1).astype(F32)
+            flow = siren(b_in, weights, "flow_imnet")
+            g = []
+            for f0 in (0, 2):
+                gx = clamp_axis((ax["base"][jx] + flow[:, f0] / F32((WW - 1.0) / 2.0)).astype(F32))
+                gy = clamp_axis((ay["base"][jy] + flow[:, f0 + 1] / F32((HH - 1.0) / 2.0)).astype(F32))
+                g.append((gy, gx))
+            (y1, x1), (y2, x2) = g
+            c_in = np.concatenate([gather_bilinear(hr_map, y1, x1), gather_bilinear(hr_map, y2, x2),
+                                   gather_bilinear(feat, y1, x1), gather_bilinear(feat, y2, x2),
+                                   gather_bilinear(fr, y1, x1), gather_bilinear(fr, y2, x2),
+                                   np.full((Q, 1), t, dtype=F32)], 1).astype(F32)
+            pred = siren(c_in, weights, "encode_imnet")
+            ret = (ret + (pred * wts[k][:, None]).astype(F32)).astype(F32)
+        out[c] = ret.T.reshape(3, HH, WW)
+    return out
+
+
 def psnr255(a: np.ndarray, b: np.ndarray) -> float:
     """``utils/util.py:140-151`` ``calculate_psnr`` on clamp(0,1)*255 images."""
     a = np.clip(a, 0, 1).astype(np.float64) * 255.0

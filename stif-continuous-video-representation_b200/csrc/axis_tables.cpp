@@ -21,19 +21,33 @@ static inline float axis_coord(int n, int j) {
   return sum;
 }
 
-void build_axis(int n_lr, int n_hr, HostAxis& o) {
+void build_axis(int n_lr, int n_hr, HostAxis& o, int shift_sign) {
   o.coord.resize(n_hr);
   o.rel.resize(n_hr);
   o.bw.resize(n_hr);
   o.base.resize(n_hr);
   o.idx.resize(n_hr);
   o.b0.resize(n_hr);
+  o.hidx.assign(shift_sign ? n_hr : 0, 0);
+  // local-ensemble shift: python double (v * (2/n_lr/2) + 1e-6) -> fp32 at the in-place tensor add (:993-994)
+  const float shift = (float)((double)shift_sign * (2.0 / (double)n_lr / 2.0) + 1e-6);
   const float lo = kClampLo, hi = kClampHi;
   for (int j = 0; j < n_hr; ++j) {
     float c = axis_coord(n_hr, j);
     c = c < lo ? lo : (c > hi ? hi : c);                           // clamp (:373)
+    float cs = c;                                                  // coordinate the gathers use
+    if (shift_sign) {
+      volatile float moved = c + shift;
+      cs = moved;
+      cs = cs < lo ? lo : (cs > hi ? hi : cs);                     // clamp_ (:995)
+      volatile float ha = cs + 1.0f;
+      volatile float hb = ha * (float)n_hr;
+      volatile float hd = hb - 1.0f;
+      volatile float hu = hd / 2.0f;
+      o.hidx[j] = (int)std::nearbyintf((float)hu);                 // nearest HR pixel of the shifted coordinate (:1026-1029)
+    }
     // grid_sampler_unnormalize, align_corners=False: ((c + 1) * n - 1) / 2, each op rounded
-    volatile float a = c + 1.0f;
+    volatile float a = cs + 1.0f;
     volatile float b = a * (float)n_lr;
     volatile float d = b - 1.0f;
     volatile float u = d / 2.0f;
@@ -55,6 +69,32 @@ void build_axis(int n_lr, int n_hr, HostAxis& o) {
     if (j == n_hr - 1 && n_hr > 1) basev = 1.0;
     o.base[j] = (float)basev;
   }
+}
+
+void ensemble_weights_host(int H, int W, int HH, int WW, float* w) {
+  HostAxis ym, yp, xm, xp;
+  build_axis(H, HH, ym, -1);
+  build_axis(H, HH, yp, +1);
+  build_axis(W, WW, xm, -1);
+  build_axis(W, WW, xp, +1);
+  const size_t Q = (size_t)HH * WW;
+  for (int jy = 0; jy < HH; ++jy)
+    for (int jx = 0; jx < WW; ++jx) {
+      const float ry[2] = {ym.rel[jy], yp.rel[jy]}, rx[2] = {xm.rel[jx], xp.rel[jx]};
+      float a[4];
+      for (int k = 0; k < 4; ++k) {                                 // (vx, vy) = (-1,-1), (-1,1), (1,-1), (1,1)
+        volatile float prod = ry[k >> 1] * rx[k & 1];
+        volatile float ar = std::fabs((float)prod) + 1e-9f;         // area + 1e-9 (:1011-1012)
+        a[k] = ar;
+      }
+      volatile float s01 = a[0] + a[1];
+      volatile float s012 = s01 + a[2];
+      volatile float tot = s012 + a[3];                             // torch.stack(areas).sum(0)
+      for (int k = 0; k < 4; ++k) {
+        volatile float wk = a[3 - k] / tot;
+        w[(size_t)k * Q + (size_t)jy * WW + jx] = wk;
+      }
+    }
 }
 
 }  // namespace stif

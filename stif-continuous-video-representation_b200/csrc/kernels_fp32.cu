@@ -131,8 +131,10 @@ __global__ void stage_a_first_layer(const float* __restrict__ tab, Geometry g, c
 
 // Stage B first layer (hoisted): f0 = sin(F + bilinear(TB; query position) + (w_t t + b))
 // reference: Sakuya_arch_test.py:406-419.
+// f_table != null (local-ensemble pass): F is gathered at the nearest HR pixel of the SHIFTED coordinate
+// (Sakuya_arch_test.py:1026-1029) from the whole-slab table instead of being the query's own value.
 __global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, Vec64 cst, long q0, long n,
-                                    float* __restrict__ f_inout) {
+                                    float* __restrict__ f_inout, const float* __restrict__ f_table) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 64) return;
   int c = (int)(i & 63);
@@ -142,7 +144,32 @@ __global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, V
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) s = fmaf(tp.w[k], tab[(long)tp.off[k] * 256 + 64 + c], s);
-  f_inout[i] = sinf(f_inout[i] + s + cst.v[c]);
+  float f = f_inout[i];
+  if (f_table) {
+    const int hy = g.y.hidx[jy], hx = g.x.hidx[jx];
+    f = (hy >= 0 && hy < g.HH && hx >= 0 && hx < g.WW) ? f_table[((long)hy * g.WW + hx) * 64 + c] : 0.f;
+  }
+  f_inout[i] = sinf(f + s + cst.v[c]);
+}
+
+// ret = ret + pred_k * (area_{3-k} / tot_area), every operation separately rounded as the reference's ATen kernels do
+// (Sakuya_arch_test.py:1011-1012, 1077-1084).  The weights are recomputed here from the per-axis rel tables.
+__global__ void ensemble_blend(const float* __restrict__ pred, float* __restrict__ out, int WW, long Q, AxisTables ym, AxisTables yp,
+                               AxisTables xm, AxisTables xp, int k) {
+  long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  const int jy = (int)(q / WW), jx = (int)(q % WW);
+  const float ry[2] = {ym.rel[jy], yp.rel[jy]}, rx[2] = {xm.rel[jx], xp.rel[jx]};
+  float a[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a[i] = __fadd_rn(fabsf(__fmul_rn(ry[i >> 1], rx[i & 1])), 1e-9f);
+  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[1]), a[2]), a[3]);
+  const float w = __fdiv_rn(a[3 - k], tot);
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float prev = k == 0 ? 0.f : out[ch * Q + q];
+    out[ch * Q + q] = __fadd_rn(prev, __fmul_rn(pred[ch * Q + q], w));
+  }
 }
 
 // Stage C+D + encode_imnet first layer (hoisted):
@@ -219,7 +246,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 64, 0), false));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
-    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c);
+    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr);
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
@@ -241,6 +268,52 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     g.scm = 1; g.scn = Qall;  // planar [3,HH,WW] (Sakuya_arch_test.py:457)
     STIF_TRY(launch_gemm(cx, g, false));
   }
+  return cudaSuccess;
+}
+
+cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw,
+                                      const Geometry geo_pass[4], const AxisTables ens_y[2], const AxisTables ens_x[2],
+                                      const Workspace& ws, float t, float* out_rgb) {
+  const Geometry& g0 = geo_pass[0];
+  const long Q = (long)g0.HH * g0.WW;
+  const float* tab = reinterpret_cast<const float*>(ws.tab);
+  float* qtab = reinterpret_cast<float*>(ws.qtab);
+  const Vec64 cA = time_constant(hw.a_t, hw.a_b, t), cB = time_constant(hw.b_t, hw.b_b, t),
+              cE = time_constant(hw.e_t, hw.e_b, t);
+  const long chunk = (long)ws.chunk;
+  for (int k = 0; k < 4; ++k) {
+    const Geometry& geo = geo_pass[k];
+    // stage A for the whole slab: F and Q tables (stage B gathers F at OTHER pixels in this mode)
+    for (long q0 = 0; q0 < Q; q0 += chunk) {
+      long n = std::min(chunk, Q - q0);
+      unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+      stage_a_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, w.a_rel, cA, q0, n, ws.act_c);
+      ++*cx.launch_counter;
+      STIF_TRY(cudaGetLastError());
+      STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 64, 1), false));
+      STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
+      STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.ftab + q0 * 64, 64, n, 64, 0), false));
+      STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
+    }
+    // stage B
+    for (long q0 = 0; q0 < Q; q0 += chunk) {
+      long n = std::min(chunk, Q - q0);
+      unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+      stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, ws.ftab);
+      ++*cx.launch_counter;
+      STIF_TRY(cudaGetLastError());
+      STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
+      STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 256, 1), false));
+      STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, n, 4, 0), false));
+    }
+    // stage C + D + E into the per-pass prediction, then the area-weighted accumulation
+    STIF_TRY(decode_slab_fp32(cx, w, hw, geo, ws, t, 0, geo.HH, 0, geo.HH, ws.pred, 2));
+    ensemble_blend<<<(unsigned)((Q + 255) / 256), 256, 0, cx.stream>>>(ws.pred, out_rgb, geo.WW, Q, ens_y[0], ens_y[1], ens_x[0],
+                                                                     ens_x[1], k);
+    ++*cx.launch_counter;
+    STIF_TRY(cudaGetLastError());
+  }
+  (void)cA;
   return cudaSuccess;
 }
 

@@ -38,6 +38,10 @@ namespace {
 using namespace tc;
 
 constexpr int kTile = 128;
+#ifndef KPOLY
+#define KPOLY 0
+#endif
+constexpr int kPolyPairs = KPOLY;   // of the 16 sine pairs per thread per chunk, this many run on the FMA pipe (poly_sin2)
 constexpr int kDephaseK1 = 0, kDephaseK2 = 0;   // default WG1 start offsets (clocks); see dephase_clocks()
 constexpr uint32_t kColA = 0;     // A-area: 256-wide activations, channel k at column k/2
 constexpr uint32_t kColAin = 96;  // 64-wide activations live in the last 32 columns of the A-area
@@ -217,6 +221,9 @@ __device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_base, uint32_t w
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// which of a thread's 16 sine pairs go to the FMA-pipe polynomial (evenly interleaved with the MUFU ones)
+__host__ __device__ constexpr bool use_poly(int j) { return ((j * kPolyPairs) % 16) < kPolyPairs; }
+
 __device__ __forceinline__ float2 ldc2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 
 // ---- epilogues (thread = query row x 32 of the chunk's 64 accumulator columns) --------------------
@@ -228,7 +235,12 @@ __device__ __forceinline__ void epi_sin_to_tmem(uint32_t src, uint32_t dst, cons
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float2 a = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), ldc2(bias + 2 * j));
-    pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
+    if (use_poly(j)) {
+      const float2 sn = poly_sin2(a);
+      pk[j] = pack_bf16x2(sn.x, sn.y);
+    } else {
+      pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
+    }
   }
   tmem_st16(dst, pk);
   tmem_st_wait();
@@ -245,8 +257,12 @@ __device__ __forceinline__ void epi_sin_fma(uint32_t src, const float* __restric
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float2 s = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), ldc2(bias + 2 * j));
-    s.x = fast_sin(s.x);
-    s.y = fast_sin(s.y);
+    if (use_poly(j)) {
+      s = poly_sin2(s);
+    } else {
+      s.x = fast_sin(s.x);
+      s.y = fast_sin(s.y);
+    }
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) acc[k] = fma2(s, ldc2(w + k * 256 + 2 * j), acc[k]);
   }
@@ -285,7 +301,12 @@ __device__ __forceinline__ void epi_flow_first_layer(uint32_t src, uint32_t dst,
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float2 a = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), make_float2(g[2 * j], g[2 * j + 1]));
-    pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
+    if (use_poly(j)) {
+      const float2 sn = poly_sin2(a);
+      pk[j] = pack_bf16x2(sn.x, sn.y);
+    } else {
+      pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
+    }
   }
   tmem_st16(dst, pk);
   tmem_st_wait();

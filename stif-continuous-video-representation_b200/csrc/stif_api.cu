@@ -41,8 +41,31 @@ size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct DeviceGeometry {
   Geometry geo{};
-  void* blob = nullptr;  // one allocation holding all axis tables
+  void* blob = nullptr;       // one allocation holding all axis tables
+  bool has_ensemble = false;  // local-ensemble tables are built lazily
+  Geometry geo_pass[4];       // pass k of decoding_localensemble: (vx,vy) = (-1,-1), (-1,1), (1,-1), (1,1)
+  AxisTables ens_y[2], ens_x[2];
+  void* ens_blob[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+
+// upload one axis (6 arrays of n entries) and return its device-side view
+int upload_axis(const HostAxis& a, int n, AxisTables* out, void** blob) {
+  const size_t stride = align256((size_t)n * 4);
+  std::vector<char> host(6 * stride, 0);
+  memcpy(host.data() + 0 * stride, a.idx.data(), (size_t)n * 4);
+  memcpy(host.data() + 1 * stride, a.rel.data(), (size_t)n * 4);
+  memcpy(host.data() + 2 * stride, a.b0.data(), (size_t)n * 4);
+  memcpy(host.data() + 3 * stride, a.bw.data(), (size_t)n * 4);
+  memcpy(host.data() + 4 * stride, a.base.data(), (size_t)n * 4);
+  if (!a.hidx.empty()) memcpy(host.data() + 5 * stride, a.hidx.data(), (size_t)n * 4);
+  CUDA_OR_RETURN(cudaMalloc(blob, host.size()));
+  CUDA_OR_RETURN(cudaMemcpy(*blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+  char* b = (char*)*blob;
+  *out = AxisTables{(const int32_t*)(b + 0 * stride), (const float*)(b + 1 * stride), (const int32_t*)(b + 2 * stride),
+                    (const float*)(b + 3 * stride), (const float*)(b + 4 * stride),
+                    a.hidx.empty() ? nullptr : (const int32_t*)(b + 5 * stride)};
+  return STIF_OK;
+}
 
 }  // namespace
 
@@ -92,6 +115,10 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
     ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
     ws.act_b = (float*)take(ws.chunk * 256 * sizeof(float));
     ws.act_c = (float*)take(ws.chunk * 64 * sizeof(float));
+    if (mode & STIF_FLAG_LOCAL_ENSEMBLE) {
+      ws.ftab = (float*)take(Q * 64 * sizeof(float));
+      ws.pred = (float*)take(Q * 3 * sizeof(float));
+    }
   } else {
     ws.chunk = Q;
   }
@@ -136,19 +163,46 @@ int get_geometry(stif_decoder* d, int H, int W, int HH, int WW, cudaStream_t str
     Geometry& g = dg.geo;
     g.H = H; g.W = W; g.HH = HH; g.WW = WW;
     g.y = AxisTables{(const int32_t*)(b + 0 * ny), (const float*)(b + 1 * ny), (const int32_t*)(b + 2 * ny),
-                     (const float*)(b + 3 * ny), (const float*)(b + 4 * ny)};
+                     (const float*)(b + 3 * ny), (const float*)(b + 4 * ny), nullptr};
     g.x = AxisTables{(const int32_t*)(b + xo + 0 * nx), (const float*)(b + xo + 1 * nx), (const int32_t*)(b + xo + 2 * nx),
-                     (const float*)(b + xo + 3 * nx), (const float*)(b + xo + 4 * nx)};
+                     (const float*)(b + xo + 3 * nx), (const float*)(b + xo + 4 * nx), nullptr};
     g.half_h = (float)((HH - 1.0) / 2.0);  // python double -> fp32 at the tensor division (warplayer.py:35-36)
     g.half_w = (float)((WW - 1.0) / 2.0);
     if (d->geos.size() > 64) {  // bounded cache (the reference's warp-grid cache is unbounded, warplayer.py:6)
-      for (auto& kv : d->geos) cudaFree(kv.second.blob);
+      for (auto& kv : d->geos) {
+        cudaFree(kv.second.blob);
+        for (void* eb : kv.second.ens_blob) if (eb) cudaFree(eb);
+      }
       d->geos.clear();
     }
     it = d->geos.emplace(key, dg).first;
   }
   *out = &it->second.geo;
   (void)stream;
+  return STIF_OK;
+}
+
+// Shifted axis tables of decoding_localensemble, built on first use for this geometry.
+int get_ensemble_geometry(stif_decoder* d, int H, int W, int HH, int WW, DeviceGeometry** out) {
+  const Geometry* base = nullptr;
+  if (int rc = get_geometry(d, H, W, HH, WW, nullptr, &base)) return rc;
+  DeviceGeometry& dg = d->geos.find(std::array<int, 4>{H, W, HH, WW})->second;
+  if (!dg.has_ensemble) {
+    for (int s = 0; s < 2; ++s) {
+      HostAxis ay, ax;
+      build_axis(H, HH, ay, s == 0 ? -1 : +1);
+      build_axis(W, WW, ax, s == 0 ? -1 : +1);
+      if (int rc = upload_axis(ay, HH, &dg.ens_y[s], &dg.ens_blob[s])) return rc;
+      if (int rc = upload_axis(ax, WW, &dg.ens_x[s], &dg.ens_blob[2 + s])) return rc;
+    }
+    for (int k = 0; k < 4; ++k) {
+      dg.geo_pass[k] = dg.geo;
+      dg.geo_pass[k].y = dg.ens_y[k >> 1];
+      dg.geo_pass[k].x = dg.ens_x[k & 1];
+    }
+    dg.has_ensemble = true;
+  }
+  *out = &dg;
   return STIF_OK;
 }
 
@@ -191,8 +245,11 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
   const int prec = mode & 0xFF;
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
-  if (mode & STIF_FLAG_LOCAL_ENSEMBLE)
-    return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE is not implemented in this build");
+  const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0;
+  if (ensemble && prec != STIF_MODE_FP32)
+    return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE is only available with STIF_MODE_FP32 in this build");
+  if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
+    return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
   if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
     return set_error(STIF_EINVAL, "invalid row band [%d,%d) halo %d for HH=%d", row_begin, row_end, halo, HH);
   const size_t need = stif_workspace_bytes(B, H, W, HH, WW, T, mode);
@@ -255,6 +312,14 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
     for (int c = 0; c < T; ++c) {
       const float t = times[(size_t)c * B + b];
       float* out_slab = out + ((size_t)c * B + b) * 3 * Q;
+      if (ensemble) {
+        DeviceGeometry* dg = nullptr;
+        if (int rc = get_ensemble_geometry(d, H, W, HH, WW, &dg)) return rc;
+        ScopedSpan sp(d, stream, 1);
+        cudaError_t e = decode_slab_fp32_ensemble(cx, d->w32, d->hw, dg->geo_pass, dg->ens_y, dg->ens_x, ws, t, out_slab);
+        if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+        continue;
+      }
       for (int stage = (band_k1 && c == 0) ? 2 : 1; stage <= 2; ++stage) {
         ScopedSpan sp(d, stream, stage);
         cudaError_t e = (prec == STIF_MODE_FP32)
@@ -323,7 +388,10 @@ int stif_create(stif_decoder_t** out, int device) {
 int stif_destroy(stif_decoder_t* d) {
   if (!d) return STIF_OK;
   cudaSetDevice(d->device);
-  for (auto& kv : d->geos) cudaFree(kv.second.blob);
+  for (auto& kv : d->geos) {
+    cudaFree(kv.second.blob);
+    for (void* eb : kv.second.ens_blob) if (eb) cudaFree(eb);
+  }
   if (d->d_w32) cudaFree(d->d_w32);
   if (d->tcw) tc_weights_destroy(d->tcw);
   if (d->host_scratch) cudaFree(d->host_scratch);
@@ -428,6 +496,13 @@ int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* re
   if (index) memcpy(index, a.idx.data(), (size_t)n_hr * 4);
   if (rel) memcpy(rel, a.rel.data(), (size_t)n_hr * 4);
   if (base) memcpy(base, a.base.data(), (size_t)n_hr * 4);
+  return STIF_OK;
+}
+
+int stif_ensemble_weights(int H, int W, int HH, int WW, float* weights_host, size_t num_floats) {
+  if (H < 1 || W < 1 || HH < 1 || WW < 1 || !weights_host) return set_error(STIF_EINVAL, "invalid argument");
+  if (num_floats < (size_t)4 * HH * WW) return set_error(STIF_EINVAL, "weights buffer too small");
+  ensemble_weights_host(H, W, HH, WW, weights_host);
   return STIF_OK;
 }
 

@@ -27,6 +27,7 @@ struct AxisTables {
   const int32_t* b0;     // [n_hr] floor of the unnormalised query coord  (stage-B bilinear, :410-417)
   const float* bw;       // [n_hr] its fractional part
   const float* base;     // [n_hr] linspace(-1,1,n_hr)                    (warplayer.py:28-31)
+  const int32_t* hidx;   // [n_hr] local-ensemble passes only: nearest HR index of the shifted coordinate (:1026-1029), else null
 };
 
 struct Geometry {

@@ -46,9 +46,13 @@ struct DeviceWeights32 {
 // Axis tables (axis_tables.cpp), host side.
 struct HostAxis {
   std::vector<float> coord, rel, bw, base;
-  std::vector<int32_t> idx, b0;
+  std::vector<int32_t> idx, b0, hidx;
 };
-void build_axis(int n_lr, int n_hr, HostAxis& out);
+// shift_sign = 0: the plain decode.  +-1: a local-ensemble pass (Sakuya_arch_test.py:981-995): every gather uses the
+// coordinate shifted by sign/n_lr + 1e-6 and re-clamped, `rel` keeps the un-shifted coordinate, `hidx` is filled.
+void build_axis(int n_lr, int n_hr, HostAxis& out, int shift_sign = 0);
+// area_k / tot_area after the reference's 0<->3, 1<->2 swap (:1078-1084): w[k*Q + q] multiplies pass k's prediction.
+void ensemble_weights_host(int H, int W, int HH, int WW, float* w /* [4, HH*WW] */);
 
 // ---------------------------------------------------------------------------------------------
 // Launch plumbing shared by the kernel translation units.
@@ -66,6 +70,8 @@ struct Workspace {
   float* act_a;   // FP32 mode only: ping-pong activation buffers [chunk,256]
   float* act_b;
   float* act_c;   // [chunk,64]
+  float* ftab;    // local-ensemble mode: F = 30 Wl0[:, :64] HRfeat for the whole slab [HH*WW,64]
+  float* pred;    // local-ensemble mode: one pass's prediction [3,HH*WW]
   int* flag;      // device int: row-band halo violation flag
   size_t chunk;   // queries per activation chunk (FP32 mode)
   size_t total_bytes;
@@ -78,6 +84,11 @@ cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const 
 cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
                              const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
                              int k1_row_end, float* out_rgb /* [3,HH,WW] */, int stage /* 1 = K1 (A+B), 2 = K2 (C+D+E) */);
+// decoding_localensemble (Sakuya_arch_test.py:962-1085): 4 shifted passes blended by swapped areas.  geo_pass[k] carries the
+// shifted axis tables of pass k (loop order (vx,vy) = (-1,-1),(-1,1),(1,-1),(1,1)); ens_y/ens_x = tables for sign -1, +1.
+cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw,
+                                      const Geometry geo_pass[4], const AxisTables ens_y[2], const AxisTables ens_x[2],
+                                      const Workspace& ws, float t, float* out_rgb);
 
 // bf16 tcgen05 path (kernels_tc.cu)
 struct TcWeights;  // opaque: device smem images + host constant blocks

@@ -29,6 +29,9 @@ __device__ __forceinline__ void fence_mbar_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -186,6 +189,35 @@ __device__ __forceinline__ float add_f16(uint16_t h, float acc) {
   float r;
   asm("add.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(acc));
   return r;
+}
+
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long r, x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b.x), "f"(b.y));
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+  float2 o;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(o.x), "=f"(o.y) : "l"(r));
+  return o;
+}
+
+// sin of two radian arguments evaluated entirely on the FMA pipe (packed fp32x2): range reduction to
+// r = x/2pi - rint(x/2pi) in [-0.5, 0.5] with the 1.5*2^23 rounding trick, then the odd degree-9 minimax
+// polynomial of sin(2 pi r) (max abs error 1.3e-5).  Used for a fraction of every epilogue's sines so
+// that the MUFU pipe (16 sines/clk/SM) and the FMA pipe share the transcendental load.
+__device__ __forceinline__ float2 poly_sin2(float2 x) {
+  const float2 inv2pi = make_float2(0.15915494309189535f, 0.15915494309189535f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f), nmagic = make_float2(-12582912.0f, -12582912.0f);
+  const float2 none = make_float2(-1.0f, -1.0f);
+  const float2 u = mul2(x, inv2pi);
+  const float2 k = add2(add2(u, magic), nmagic);
+  const float2 r = fma2(k, none, u);
+  const float2 s = mul2(r, r);
+  float2 p = fma2(s, make_float2(32.1492805f, 32.1492805f), make_float2(-74.1115570f, -74.1115570f));
+  p = fma2(p, s, make_float2(81.2946777f, 81.2946777f));
+  p = fma2(p, s, make_float2(-41.3257561f, -41.3257561f));
+  p = fma2(p, s, make_float2(6.28293371f, 6.28293371f));
+  return mul2(p, r);
 }
 
 // fast sine on the MUFU pipe (abs error ~5e-7 for |x| <~ 100; the result is rounded to bf16 anyway)

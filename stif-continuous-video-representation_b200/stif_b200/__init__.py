@@ -5,7 +5,8 @@ Drop-in for ONE path of paperwave/STIF-continuous-video-representation: ``LunaTo
 ``lib/libstif_b200.so`` (hand-written CUDA behind the C ABI of ``include/stif_b200.h``);
 this package is the thin host side.  Importing it without the built library raises.
 """
-from ._lib import LIB_PATH, STIF_MODE_BF16, STIF_MODE_FP32, StifError, axis_tables, selftest  # noqa: F401
+from ._lib import (LIB_PATH, STIF_MODE_BF16, STIF_MODE_FP32, StifError, axis_tables, ensemble_weights,  # noqa: F401
+                   selftest)
 from .decoder import (STIFQueryDecoder, install_class_patch, patch_reference_model,  # noqa: F401
                       weight_keys)
 

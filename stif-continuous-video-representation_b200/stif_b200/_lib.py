@@ -22,7 +22,7 @@ STIF_ABI_VERSION = 1
 EXPORTS = [
     "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
     "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_axis_tables",
-    "stif_debug_last_flow", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
+    "stif_ensemble_weights", "stif_debug_last_flow", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
 ]
 
 
@@ -50,6 +50,7 @@ def _load():
                                      C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]
     lib.stif_decode_host.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, vp]
     lib.stif_axis_tables.argtypes = [C.c_int, C.c_int, fp, ip, fp, fp]
+    lib.stif_ensemble_weights.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t]
     lib.stif_debug_last_flow.argtypes = [vp, fp, C.c_size_t]
     lib.stif_launch_count.argtypes = [vp]
     lib.stif_launch_count.restype = C.c_int64
@@ -83,6 +84,15 @@ def axis_tables(n_lr: int, n_hr: int):
     check(lib.stif_axis_tables(n_lr, n_hr, coord.ctypes.data_as(fp), index.ctypes.data_as(ip),
                                rel.ctypes.data_as(fp), base.ctypes.data_as(fp)))
     return {"coord": coord, "index": index, "rel": rel, "base": base}
+
+
+def ensemble_weights(H: int, W: int, HH: int, WW: int):
+    """decoding_localensemble's blend weights [4, HH*WW] (host computation, bit-exact contract)."""
+    import numpy as np
+
+    w = np.empty((4, HH * WW), np.float32)
+    check(lib.stif_ensemble_weights(H, W, HH, WW, w.ctypes.data_as(C.POINTER(C.c_float)), w.size))
+    return w
 
 
 def selftest(device: int = 0) -> tuple[int, str]:

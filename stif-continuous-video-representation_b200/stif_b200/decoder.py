@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
+from ._lib import STIF_FLAG_LOCAL_ENSEMBLE, STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
 
 _MODES = {"bf16": STIF_MODE_BF16, "fp32": STIF_MODE_FP32}
 
@@ -148,7 +148,7 @@ class STIFQueryDecoder(torch.nn.Module):
 
     def decode_stacked(self, latent, frames, times, scale=None, mode: str | None = None,
                        rows: tuple[int, int] | None = None, halo: int = 0,
-                       out: torch.Tensor | None = None) -> torch.Tensor:
+                       out: torch.Tensor | None = None, local_ensemble: bool = False) -> torch.Tensor:
         """Decode to one ``[T,B,3,HH,WW]`` tensor.  ``rows=(r0,r1)`` restricts the call to a row band
         (``stif_decode_rows``), used by the sharding launcher."""
         if not self._loaded:
@@ -156,7 +156,7 @@ class STIFQueryDecoder(torch.nn.Module):
         latent, frames, B, H, W, HH, WW = self._prep(latent, frames, scale)
         tm = _times_matrix(times, B)
         T = tm.shape[0]
-        m = _MODES[mode or self.mode]
+        m = _MODES[mode or self.mode] | (STIF_FLAG_LOCAL_ENSEMBLE if local_ensemble else 0)
         ws = self._workspace_for(B, H, W, HH, WW, T, m)
         if out is None:
             out = torch.empty((T, B, 3, HH, WW), dtype=torch.float32, device=self.device)
@@ -177,6 +177,13 @@ class STIFQueryDecoder(torch.nn.Module):
     def decode(self, latent, frames, times, scale=None, mode: str | None = None) -> list[torch.Tensor]:
         """``LunaTokis.decoding`` return convention: list of ``T`` tensors ``[B,3,HH,WW]``."""
         return list(self.decode_stacked(latent, frames, times, scale, mode).unbind(0))
+
+    def decode_localensemble(self, latent, frames, times, scale=None) -> torch.Tensor:
+        """``LunaTokis.decoding_localensemble`` (``Sakuya_arch_test.py:962-1085``): four shifted passes blended by
+        swapped areas; batch size 1, returns ``[T,3,HH,WW]``.  fp32 kernels only in this build."""
+        if latent.shape[0] != 1:
+            raise ValueError("decoding_localensemble requires batch size 1 (Sakuya_arch_test.py:989)")
+        return self.decode_stacked(latent, frames, list(times), scale, mode="fp32", local_ensemble=True)[:, 0]
 
     def decode_host(self, latent: np.ndarray | torch.Tensor, frames, times, scale=None, mode: str | None = None,
                     out: torch.Tensor | None = None) -> torch.Tensor:
@@ -297,6 +304,7 @@ def patch_reference_model(model, mode: str = "bf16"):
 
     model.decoding = decoding
     model.decoding_fasttest = decoding_fasttest
+    model.decoding_localensemble = lambda times=None, scale=None: dec.decode_localensemble(model.feat, model.inp, times, scale)
     model.decoding_fasttest_memory = decoding_fasttest
     model.stif_decoder = dec
     model.stif_refresh_weights = lambda: dec.load_weights(_decoder_state(model))

@@ -45,6 +45,18 @@ def test_axis_tables_bit_exact_vs_torch_fixtures(stif):
         assert np.array_equal(t["base"], o["base"])
 
 
+def test_ensemble_weights_bit_exact_vs_reference(stif):
+    """area/tot_area of decoding_localensemble, captured from the reference run (oracle/make_goldens.py): bit-exact."""
+    from oracle.make_goldens import CASES
+    for name, cfg in CASES.items():
+        if cfg["B"] != 1:
+            continue
+        g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+        HH, WW = g["rgb"].shape[-2:]
+        w = stif.ensemble_weights(cfg["H"], cfg["W"], HH, WW)
+        assert np.array_equal(w, g["ensemble_weights"]), name
+
+
 def test_axis_tables_reject_bad_sizes(stif):
     with pytest.raises(stif.StifError):
         stif.axis_tables(0, 16)

@@ -65,6 +65,18 @@ def test_fasttest_is_the_same_function(name):
     assert np.array_equal(g["rgb_fasttest"], g["rgb"][:, 0])
 
 
+@pytest.mark.parametrize("name", [n for n in CASES if CASES[n]["B"] == 1])
+def test_localensemble_restatement(name):
+    """decoding_localensemble (Sakuya_arch_test.py:962-1085): RGB and the bit-exact blend weights."""
+    cfg = CASES[name]
+    g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+    w, lat, fr = _inputs(cfg)
+    out = R.decode_localensemble(lat, fr, w, cfg["times"], cfg["scale"])
+    assert np.abs(out - g["rgb_localensemble"]).max() <= FP32_TOL
+    HH, WW = out.shape[-2:]
+    assert np.array_equal(R.ensemble_weights(cfg["H"], cfg["W"], HH, WW), g["ensemble_weights"])
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_torch_port(name):
     cfg = CASES[name]

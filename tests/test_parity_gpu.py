@@ -140,6 +140,20 @@ def test_properties_at_config2_size(mode, decoders):
     assert err <= 2e-2
 
 
+@pytest.mark.parametrize("name", [n for n in CASES if CASES[n]["B"] == 1])
+def test_localensemble_mode(name, decoders):
+    """decoding_localensemble through STIF_FLAG_LOCAL_ENSEMBLE against the reference's own output (fp32 kernels)."""
+    cfg = CASES[name]
+    g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+    lat, fr = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    dec = decoders(cfg["wseed"], cfg["stress"], "fp32")
+    out = dec.decode_localensemble(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), cfg["times"], cfg["scale"])
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - g["rgb_localensemble"]).max()
+    print(f"{name} local-ensemble: max-abs {err:.3e} (differs from plain decode by {np.abs(g['rgb_localensemble'] - g['rgb'][:, 0]).max():.2e})")
+    assert err <= 1e-4
+
+
 def test_band_halo_violation_is_reported(decoders, stif):
     lat, fr = synth.make_inputs(1, 1, 16, 16, 0.05)
     dec = decoders(1, True, "fp32")                                   # stress weights: flows of ~13 px
