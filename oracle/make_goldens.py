@@ -143,6 +143,36 @@ def run_config1(stress: bool) -> dict:
             "weight_checksum": np.float64(checksum(*weights.values()))}
 
 
+def run_e2e_small() -> dict:
+    """The caller's path of BASELINE.json config 5 in miniature: `custom_video_test.single_forward` (:41-54) pads the
+    frame pair to a multiple of 4, builds `time_Tensors = [tensor([i/8])[None] for i in range(8)]` and calls
+    `model(imgs, times)` = `gen_feat` (reference encoder, here through a torchvision-backed `_ext`) + `decoding`.
+    Stored: the encoder's latent (what the drop-in decoder receives), the padded frames and the reference's RGB."""
+    import importlib.util
+    import torch
+
+    spec = importlib.util.spec_from_file_location("rcvt", os.path.join(ROOT, "tools", "run_custom_video_test.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    sys.modules["_ext"] = tool.make_ext_shim()
+    weights = synth.make_weights(4, True)
+    model = build_reference_model(weights)                      # encoder: torch.manual_seed(0) random init
+    clear_warp_cache()
+    rng = np.random.default_rng(77)
+    h, w = 26, 34                                               # not multiples of 4 -> padded to 28 x 36
+    frames = rng.random((1, 2, 3, h, w), dtype=np.float32)
+    imgs = torch.from_numpy(frames)
+    H, W = (h + 3) // 4 * 4, (w + 3) // 4 * 4
+    padded = torch.zeros(1, 2, 3, H, W)
+    padded[:, :, :, :h, :w] = imgs                              # custom_video_test.py:44-48
+    times = [torch.tensor([i / 8.0])[None] for i in range(8)]   # :50
+    with torch.no_grad():
+        out = model(padded, times)                              # LunaTokis.forward -> gen_feat + decoding (:1222-1231)
+    rgb = np.stack([o.numpy() for o in out], 0)                 # [8,1,3,4H,4W]
+    return {"latent": model.feat.numpy().astype(np.float32), "frames": padded.numpy().astype(np.float32),
+            "rgb": rgb.astype(np.float32), "weight_checksum": np.float64(checksum(*weights.values()))}
+
+
 def axis_goldens() -> dict:
     """Per-axis nearest indices straight from ``F.grid_sample(mode='nearest')`` on an index ramp,
     the ``make_coord`` axes and ``torch.linspace`` for every (n_lr, n_hr) pair."""
@@ -175,6 +205,7 @@ def main():
         res = run_config1(stress)
         np.savez_compressed(os.path.join(GOLD, f"config1_{'stress' if stress else 'init'}.npz"), **res)
         print("config1", stress, res["absmax"])
+    np.savez_compressed(os.path.join(GOLD, "e2e_small.npz"), **run_e2e_small())
     np.savez_compressed(os.path.join(GOLD, "axis_tables.npz"), **axis_goldens())
     print("done")
 

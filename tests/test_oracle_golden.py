@@ -86,6 +86,16 @@ def test_torch_port(name):
     assert np.abs(rgb - g["rgb"]).max() <= FP32_TOL
 
 
+def test_e2e_small_encoder_latents():
+    """Config 5 in miniature: latents produced by the reference ENCODER (gen_feat through a torchvision `_ext` shim) for
+    a padded frame pair, decoded at t = i/8 as custom_video_test.py:44-52 does."""
+    g = np.load(os.path.join(GOLD, "e2e_small.npz"))
+    w = synth.make_weights(4, True)
+    assert checksum(*w.values()) == pytest.approx(float(g["weight_checksum"]), rel=1e-12)
+    out = R.decode(g["latent"], g["frames"], w, [i / 8.0 for i in range(8)], None)
+    assert np.abs(out - g["rgb"]).max() <= FP32_TOL
+
+
 def test_axis_tables_bit_exact():
     a = np.load(os.path.join(GOLD, "axis_tables.npz"))
     for n_lr, n_hr in a["pairs"]:

@@ -154,6 +154,35 @@ def test_localensemble_mode(name, decoders):
     assert err <= 1e-4
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_config5_caller_path_small(mode, decoders):
+    """Encoder-produced latents + padded frames + the 8 time tensors of custom_video_test.py:44-52, against the
+    reference's own model(imgs, times) output (tests/golden/e2e_small.npz)."""
+    g = np.load(os.path.join(GOLD, "e2e_small.npz"))
+    dec = decoders(4, True, mode)
+    times = [torch.tensor([i / 8.0])[None] for i in range(8)]                 # exactly the caller's time_Tensors (:50)
+    out = dec.decode(torch.from_numpy(g["latent"]).cuda(), torch.from_numpy(g["frames"]).cuda(), times)
+    assert isinstance(out, list) and len(out) == 8 and tuple(out[0].shape) == (1, 3, 112, 144)
+    rgb = torch.stack(out, 0).cpu().numpy()
+    err = np.abs(rgb - g["rgb"]).max()
+    d = abs(R.psnr255(rgb, g["rgb"] + 0.02) - R.psnr255(g["rgb"], g["rgb"] + 0.02))
+    print(f"config5-small {mode}: max-abs {err:.3e}, PSNR(new,ref) {R.psnr255(rgb, g['rgb']):.1f} dB")
+    assert err <= TOL[mode]
+
+
+def test_config5_shape_properties(decoders):
+    """Config 5's decode shape (480x272 padded latent -> 1088x1920, 8 timesteps): determinism and bf16/fp32 agreement on
+    one frame pair; sizes where the oracle cannot run."""
+    lat, fr = synth.smooth_inputs(21, 1, 272, 480, 0.05)
+    times = [i / 8.0 for i in range(8)]
+    a = _run(decoders(0, True, "bf16"), lat, fr, times, None)
+    assert a.shape == (8, 1, 3, 1088, 1920) and np.isfinite(a).all()
+    b = _run(decoders(0, True, "bf16"), lat, fr, times[3:5], None)
+    assert np.array_equal(a[3:5], b)
+    c = _run(decoders(0, True, "fp32"), lat, fr, times[3:4], None)
+    assert np.abs(a[3] - c[0]).max() <= 2e-2
+
+
 def test_band_halo_violation_is_reported(decoders, stif):
     lat, fr = synth.make_inputs(1, 1, 16, 16, 0.05)
     dec = decoders(1, True, "fp32")                                   # stress weights: flows of ~13 px
