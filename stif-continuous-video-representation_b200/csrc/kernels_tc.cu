@@ -200,11 +200,15 @@ __device__ __forceinline__ void layer_begin(WgCtx& cx, uint32_t a_base, uint32_t
 }
 template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf, class Epi>
 __device__ __forceinline__ void layer_finish(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
+  // The accumulator of chunk i+1 is fetched (tcgen05.ld, asynchronous) as soon as chunk i's registers are dead, so its
+  // TMEM round trip and mbarrier wake-up hide behind chunk i's store / fence / barrier / MMA issue.
+  uint32_t v[32];
+  tmem_ld32(wait_chunk(cx), v);
 #pragma unroll
   for (int i = 0; i < NC; ++i) {
-    const uint32_t d = wait_chunk(cx);
+    tmem_ld_wait();
     trace_mark(cx, 10 + i);
-    epi(i, d);
+    epi(i, v, [&]() { if (i + 1 < NC) tmem_ld32(wait_chunk(cx), v); });
     trace_mark(cx, 20 + i);
     tc_fence_before();
     wg_barrier(cx.wg);
@@ -230,10 +234,9 @@ __device__ __forceinline__ float4 ldc4(const float* p) { return *reinterpret_cas
 
 // ---- epilogues (thread = query row x 32 of the chunk's 64 accumulator columns) --------------------
 // act = sin(acc + bias) -> bf16 -> TMEM A operand (16 columns at dst)
-__device__ __forceinline__ void epi_sin_to_tmem(uint32_t src, uint32_t dst, const float* __restrict__ bias) {
-  uint32_t v[32], pk[16];
-  tmem_ld32(src, v);
-  tmem_ld_wait();
+template <class Pf>
+__device__ __forceinline__ void epi_sin_to_tmem(uint32_t (&v)[32], uint32_t dst, const float* __restrict__ bias, Pf&& next_ld) {
+  uint32_t pk[16];
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 b4 = ldc4(bias + 4 * j4);
@@ -250,18 +253,16 @@ __device__ __forceinline__ void epi_sin_to_tmem(uint32_t src, uint32_t dst, cons
       }
     }
   }
+  next_ld();
   tmem_st16(dst, pk);
   tmem_st_wait();
 }
 
 // act = sin(acc + bias) kept in fp32 and contracted with the NOUT x 256 output layer on the FMA pipe.
 // acc[k] holds (even-column, odd-column) partial sums.
-template <int NOUT>
-__device__ __forceinline__ void epi_sin_fma(uint32_t src, const float* __restrict__ bias, const float* __restrict__ w,
-                                            float2 (&acc)[NOUT]) {
-  uint32_t v[32];
-  tmem_ld32(src, v);
-  tmem_ld_wait();
+template <int NOUT, class Pf>
+__device__ __forceinline__ void epi_sin_fma(uint32_t (&v)[32], const float* __restrict__ bias, const float* __restrict__ w,
+                                            float2 (&acc)[NOUT], Pf&& next_ld) {
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 b4 = ldc4(bias + 4 * j4);
@@ -283,6 +284,7 @@ __device__ __forceinline__ void epi_sin_fma(uint32_t src, const float* __restric
       for (int k = 0; k < NOUT; ++k) acc[k] = fma2(s, h ? make_float2(w4[k].z, w4[k].w) : make_float2(w4[k].x, w4[k].y), acc[k]);
     }
   }
+  next_ld();
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
@@ -291,30 +293,28 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 // acc + bias -> fp16 -> 64 bytes of the projected HR table
-__device__ __forceinline__ void epi_store_qtab(uint32_t src, const float* __restrict__ bias, __half* dst, bool valid) {
-  uint32_t v[32];
-  tmem_ld32(src, v);
-  tmem_ld_wait();
+template <class Pf>
+__device__ __forceinline__ void epi_store_qtab(uint32_t (&v)[32], const float* __restrict__ bias, __half* dst, bool valid, Pf&& next_ld) {
+  uint32_t o[16];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b4 = ldc4(bias + 4 * j4);
+    const float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
+    const float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
+    o[2 * j4] = pack_half2(a0.x, a0.y);
+    o[2 * j4 + 1] = pack_half2(a1.x, a1.y);
+  }
+  next_ld();
   if (!valid) return;
   uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint32_t o[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 a = add2(make_float2(__uint_as_float(v[8 * j + 2 * e]), __uint_as_float(v[8 * j + 2 * e + 1])),
-                            ldc2(bias + 8 * j + 2 * e));
-      o[e] = pack_half2(a.x, a.y);
-    }
-    d4[j] = make_uint4(o[0], o[1], o[2], o[3]);
-  }
+  for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
 }
 
 // f0 = sin(F + g) -> bf16 -> TMEM (g already holds bilinear(TB) + time constant + composed bias)
-__device__ __forceinline__ void epi_flow_first_layer(uint32_t src, uint32_t dst, const float (&g)[32]) {
-  uint32_t v[32], pk[16];
-  tmem_ld32(src, v);
-  tmem_ld_wait();
+template <class Pf>
+__device__ __forceinline__ void epi_flow_first_layer(uint32_t (&v)[32], uint32_t dst, const float (&g)[32], Pf&& next_ld) {
+  uint32_t pk[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float2 a = add2(make_float2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), make_float2(g[2 * j], g[2 * j + 1]));
@@ -325,6 +325,7 @@ __device__ __forceinline__ void epi_flow_first_layer(uint32_t src, uint32_t dst,
       pk[j] = pack_bf16x2(fast_sin(a.x), fast_sin(a.y));
     }
   }
+  next_ld();
   tmem_st16(dst, pk);
   tmem_st_wait();
 }
@@ -514,9 +515,9 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
 
     // ---- feat_imnet hidden layers
     run_layer<1, 4, false>(cx, cx.tmem + kColAin, wsm + k1F1, 64, [](int) { return 0; },
-                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0); });
-    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t d) {
-      epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0);
+                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
+    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
     });
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
@@ -548,17 +549,17 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     }
 
     trace_mark(cx, 4);
-    layer_finish<3, 16, false>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t d) {
-      if (i < 2) epi_store_qtab(d, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid);
-      else epi_flow_first_layer(d, cx.lane_addr + kColAin + CH * 16, gB);
+    layer_finish<3, 16, false>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if (i < 2) epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
+      else epi_flow_first_layer(v, cx.lane_addr + kColAin + CH * 16, gB, pf);
     });
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
     run_layer<1, 4, false>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
-                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0); });
+                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
-                 [&](int i, uint32_t d) { epi_sin_fma<4>(d, p.c.l2_b + 64 * i + ch0, p.c.l3_w + 64 * i + ch0, fl); });
+                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, p.c.l3_w + 64 * i + ch0, fl, pf); });
     // combine the two column halves and store
     const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
     if (CH == 1) part[cx.row] = mine;
@@ -722,13 +723,13 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
 
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
     run_layer<1, 4, true>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
-                 [&](int, uint32_t d) { epi_sin_to_tmem(d, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0); });
-    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t d) {
-      epi_sin_to_tmem(d, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0);
+                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
+    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
-                 [&](int i, uint32_t d) { epi_sin_fma<3>(d, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb); });
+                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb, pf); });
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
     wg_barrier(cx.wg);
