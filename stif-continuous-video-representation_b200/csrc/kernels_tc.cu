@@ -478,7 +478,8 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
   float4* part = reinterpret_cast<float4*>(smem + k1Part) + cx.wg * 128;
   const int ch0 = CH * 32;   // this thread's 32 channels of every 64-wide vector
 
-  for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
+  const long tile_first = (long)blockIdx.x * 2 + cx.wg;
+  for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;   // trace the first 16 tiles only
     const long q = p.q_begin + tile * kTile + cx.row;
     const bool valid = q < p.q_end;
@@ -594,10 +595,9 @@ __global__ void __launch_bounds__(512, 1) k1_stage_ab_kernel(const __grid_consta
 // 1.5 KB of shared memory.  Phase 2: 8 lanes per query, 8 channels per lane: every tap is a
 // 16-byte load (one 128-byte line per query), blended with mixed-precision FMAs (fp16 table value
 // x fp16 weight + fp32 accumulator), then sine -> bf16 -> the SW128 A tile of the first MMA.
-__device__ __forceinline__ void k2_gather(const K2Params& p, uint8_t* a0, uint4* stg, long tile_q0, int warp_in_wg, int lane) {
+// phase 1 (bilinear footprints -> per-warp staging); issued one tile ahead, under the 256->256 layer's first MMA wait
+__device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile_q0, int warp_in_wg, int lane) {
   const Geometry& g = p.g;
-  const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
-  const char* __restrict__ tab_b = reinterpret_cast<const char*>(p.tab);
   {
     const int qi = lane & 15, which = lane >> 4;
     const long q = min(tile_q0 + warp_in_wg * 16 + qi, p.q_end - 1);
@@ -625,6 +625,12 @@ __device__ __forceinline__ void k2_gather(const K2Params& p, uint8_t* a0, uint4*
                                 pack_half2(lr.w[2], lr.w[3]));
   }
   __syncwarp();
+}
+
+// phase 2 (loads + blend + sine -> A tile)
+__device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane) {
+  const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
+  const char* __restrict__ tab_b = reinterpret_cast<const char*>(p.tab);
   const int sub = lane & 7;
   float cE[8];
 #pragma unroll
@@ -690,11 +696,13 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warp_in_wg = warp & 7;
   uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
   uint4* stg = reinterpret_cast<uint4*>(smem + k2Taps + warp * 1536);
-  float4* part = reinterpret_cast<float4*>(smem + k2Taps + cx.wg * 8 * 1536);   // reuses the WG's tap staging
+  float4* part = reinterpret_cast<float4*>(a0);   // partial-sum exchange reuses the WG's A tile (dead after the first MMA)
   const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
   const int ch0 = CH * 32;
 
-  for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
+  const long tile_first = (long)blockIdx.x * 2 + cx.wg;
+  if (tile_first < ntiles) k2_gather_taps(p, stg, p.q_begin + tile_first * kTile, warp_in_wg, lane);
+  for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
     const long tile_q0 = p.q_begin + tile * kTile;
     const long q = tile_q0 + cx.row;
@@ -714,7 +722,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
         if (CH == 0) prefetch_l2(reinterpret_cast<const float4*>(p.flow) + qn);
       }
     }
-    k2_gather(p, a0, stg, tile_q0, warp_in_wg, lane);
+    k2_gather_blend(p, a0, stg, warp_in_wg, lane);
     trace_mark(cx, 2);
     fence_proxy_async_smem();
     tc_fence_before();
@@ -728,7 +736,12 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
+    layer_begin<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
+    {  // footprints of this WG's next tile, computed while the first 256->256 chunk is on the tensor pipe
+      const long tile_next = tile + (long)gridDim.x * 2;
+      if (tile_next < ntiles) k2_gather_taps(p, stg, p.q_begin + tile_next * kTile, warp_in_wg, lane);
+    }
+    layer_finish<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb, pf); });
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
@@ -739,7 +752,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
       p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
       p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
     }
-    // the next tile's gather rewrites the staging area `part` aliases: every reader must be done
+    // the next tile's gather rewrites the A tile `part` aliases: every reader must be done
     wg_barrier(cx.wg);
   }
 }
