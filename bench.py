@@ -159,7 +159,7 @@ def main_ours(args):
     import torch.distributed as dist
 
     import stif_b200
-    from oracle import synth  # seeded synthetic inputs only (fixture generator, not the checker)
+    from stif_b200 import synthetic as synth  # seeded numpy generators (product-side helper; nothing from oracle/ here)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -264,9 +264,15 @@ def main_ours(args):
     flop_launch = (FLOP_K1 if dom.startswith("K1") else FLOP_K2) * HH * WW
     achieved = flop_launch / (per[dom] * 1e-3) / 1e12
     kernel_ms = sum(prof["ms"]) / args.steps
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (config 2 only)
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if args.workload == "config2" and os.path.isfile(tpath):
+        t = json.load(open(tpath)).get(dom)
+        if t:
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
     roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
             "frac": achieved / peak_burst, "peak_source": f"{peak_src} (burst; sustained {peak_sust})",
-            "traffic": None, "ms_per_launch": per[dom],
+            "traffic": traffic, "ms_per_launch": per[dom],
             "all_kernels_ms_per_launch": per,
             "share_of_step": {n: per[n] * prof["count"][groups[n]] / args.steps / kernel_ms for n in per},
             "whole_step_frac": qps / world * FLOP_PER_QUERY / 1e12 / peak_burst}
