@@ -95,7 +95,10 @@ struct K2Params {
   float* out;          // [3, plane]
   long plane;
   const uint8_t* wimg;
-  long q_begin, q_end;
+  int row_begin, row_end;   // output rows this launch decodes
+  int tiles_x;              // K2 tiles are 8 rows x 16 columns (2 x 4 warp patches of 4 x 4 queries): neighbouring
+                            // queries of a warp share bilinear taps in x AND y, so the L1 / in-flight-miss merge removes
+                            // most of the duplicate line requests of the gather
   int band_lo, band_hi, band_mode;
   int* flag;
   long long* trace;
@@ -595,12 +598,24 @@ __global__ void __launch_bounds__(512, 1) k1_stage_ab_kernel(const __grid_consta
 // 1.5 KB of shared memory.  Phase 2: 8 lanes per query, 8 channels per lane: every tap is a
 // 16-byte load (one 128-byte line per query), blended with mixed-precision FMAs (fp16 table value
 // x fp16 weight + fp32 accumulator), then sine -> bf16 -> the SW128 A tile of the first MMA.
+// K2 tile geometry: row r (0..127) of tile `tile` -> linear query index (clamped into the launch's rows / the raster so
+// that loads stay in range; `valid` says whether the query really exists).
+__device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bool& valid) {
+  const int ty = (int)(tile / p.tiles_x), tx = (int)(tile - (long)ty * p.tiles_x);
+  const int patch = r >> 4, i = r & 15;
+  const int y = p.row_begin + ty * 8 + (patch >> 2) * 4 + (i >> 2);
+  const int x = tx * 16 + (patch & 3) * 4 + (i & 3);
+  valid = (y < p.row_end) & (x < p.g.WW);
+  return (long)min(y, p.row_end - 1) * p.g.WW + min(x, p.g.WW - 1);
+}
+
 // phase 1 (bilinear footprints -> per-warp staging); issued one tile ahead, under the 256->256 layer's first MMA wait
-__device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile_q0, int warp_in_wg, int lane) {
+__device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile, int warp_in_wg, int lane) {
   const Geometry& g = p.g;
   {
     const int qi = lane & 15, which = lane >> 4;
-    const long q = min(tile_q0 + warp_in_wg * 16 + qi, p.q_end - 1);
+    bool valid_;
+    const long q = k2_query(p, tile, warp_in_wg * 16 + qi, valid_);
     const int jy = (int)(q / g.WW), jx = (int)(q - (long)jy * g.WW);
     const float4 fl = __ldg(reinterpret_cast<const float4*>(p.flow) + q);
     float gy, gx;
@@ -697,23 +712,23 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
   uint4* stg = reinterpret_cast<uint4*>(smem + k2Taps + warp * 1536);
   float4* part = reinterpret_cast<float4*>(a0);   // partial-sum exchange reuses the WG's A tile (dead after the first MMA)
-  const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
+  const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
   const int ch0 = CH * 32;
 
   const long tile_first = (long)blockIdx.x * 2 + cx.wg;
-  if (tile_first < ntiles) k2_gather_taps(p, stg, p.q_begin + tile_first * kTile, warp_in_wg, lane);
+  if (tile_first < ntiles) k2_gather_taps(p, stg, tile_first, warp_in_wg, lane);
   for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
-    const long tile_q0 = p.q_begin + tile * kTile;
-    const long q = tile_q0 + cx.row;
-    const bool valid = q < p.q_end;
+    bool valid;
+    const long q = k2_query(p, tile, cx.row, valid);
 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
     trace_mark(cx, 1);
     {  // L2 prefetch for this WG's NEXT tile: the lines a small flow would touch (own pixel, rows -1/0/+1).
        // Pure hint: a wrong guess costs nothing but the prefetch itself.
-      const long qn = tile_q0 + (long)gridDim.x * 2 * kTile + cx.row;
-      if (qn < p.q_end) {
+      bool vn;
+      const long qn = k2_query(p, tile + (long)gridDim.x * 2, cx.row, vn);
+      if (vn && tile + (long)gridDim.x * 2 < ntiles) {
         const char* base = reinterpret_cast<const char*>(p.qtab) + CH * 128;
         const long W2 = (long)p.g.WW;
         prefetch_l2(base + qn * 256);
@@ -739,7 +754,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     layer_begin<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
     {  // footprints of this WG's next tile, computed while the first 256->256 chunk is on the tensor pipe
       const long tile_next = tile + (long)gridDim.x * 2;
-      if (tile_next < ntiles) k2_gather_taps(p, stg, p.q_begin + tile_next * kTile, warp_in_wg, lane);
+      if (tile_next < ntiles) k2_gather_taps(p, stg, tile_next, warp_in_wg, lane);
     }
     layer_finish<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb, pf); });
@@ -940,13 +955,14 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.out = out_rgb;
   p.plane = (long)geo.HH * geo.WW;
   p.wimg = tw->d_k2;
-  p.q_begin = row_begin * WW;
-  p.q_end = row_end * WW;
+  p.row_begin = row_begin;
+  p.row_end = row_end;
+  p.tiles_x = (geo.WW + 15) / 16;
   p.band_lo = k1_row_begin;
   p.band_hi = k1_row_end;
   p.band_mode = (k1_row_begin > 0 || k1_row_end < geo.HH) ? 1 : 0;
   p.flag = ws.flag;
-  const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
+  const long ntiles = (long)p.tiles_x * ((row_end - row_begin + 7) / 8);
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
   p.trace = trace_buffer();
   p.dephase_clk = dephase_clocks(2);
