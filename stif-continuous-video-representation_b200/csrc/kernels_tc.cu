@@ -120,8 +120,9 @@ struct WgCtx {
   uint32_t tmem;       // TMEM address of this WG's column 0, lane 0
   uint32_t lane_addr;  // same + this warp's lane quarter (for tcgen05.ld/st)
   uint64_t* full;      // two mbarriers: accumulator slot s is complete
-  uint32_t n_issued, n_waited;
+  uint32_t n_issued, n_waited, n_steps;
   int wg, tid_wg, warp_in_wg, row, colhalf;
+  bool issuer;         // this warp only issues the WG's MMAs (warps 16, 17); the other 8 warps of the WG only run epilogues
   long long* trace;    // this thread's trace cursor (null unless tracing)
 };
 
@@ -139,7 +140,18 @@ __device__ __forceinline__ void trace_mark(WgCtx& cx, int tag) {
 #endif
 }
 
-__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
+// Named barriers.  Per WG: two alternating "step" barriers (ids 1..4, 288 threads = 8 epilogue warps that only ARRIVE
+// + the issuer warp that SYNCs: the epilogue warps never wait for each other, only for accumulators), and one
+// epilogue-only barrier (ids 5, 6, 256 threads) for the rare smem exchanges.  A warp can run at most one step ahead of
+// the slowest warp of its WG (step s+2's accumulator is issued only after everyone arrived for step s), hence two ids.
+__device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 5) : "memory"); }
+template <bool ISSUER>
+__device__ __forceinline__ void step_done(WgCtx& cx) {
+  const int id = 1 + cx.wg * 2 + (int)(cx.n_steps & 1);
+  if (ISSUER) asm volatile("bar.sync %0, 288;" ::"r"(id) : "memory");
+  else asm volatile("bar.arrive %0, 288;" ::"r"(id) : "memory");
+  ++cx.n_steps;
+}
 
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the warp in hardware for a bounded time, so this loop turns only a few times per wait; the
@@ -158,10 +170,10 @@ __device__ __forceinline__ bool elect_one() {
 // the WG with warp-uniform operands (one elected lane issues), so the descriptors live in uniform
 // registers and each tcgen05.mma costs a couple of instructions.
 //   A_SMEM: A operand is an SW128 tile in shared memory at a_base (K = 64); else A is in TMEM at address a_base.
-template <int KSTEPS, bool A_SMEM>
+template <int KSTEPS, bool A_SMEM, bool ISSUER>
 __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, int chunk) {
   const uint32_t slot = cx.n_issued & 1;
-  if (cx.warp_in_wg == 0) {
+  if (ISSUER) {
     tc_fence_after();
     const uint32_t idesc = make_idesc_bf16(128, 64);
     const uint32_t d = cx.tmem + kColD + slot * 64;
@@ -196,33 +208,40 @@ __device__ __forceinline__ uint32_t wait_chunk(WgCtx& cx) {
 // placed between the first MMA issue and the first wait.
 // Preconditions of layer_begin: the A operand is complete and a WG barrier has been passed since it
 // was written and since both accumulator slots were last read.
-template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf>
+template <int NC, int KSTEPS, bool A_SMEM, bool ISSUER, class ChunkOf>
 __device__ __forceinline__ void layer_begin(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of) {
-  issue_chunk<KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of(0));
-  if (NC > 1) issue_chunk<KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of(1));
+  issue_chunk<KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of(0));
+  if (NC > 1) issue_chunk<KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of(1));
 }
-template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf, class Epi>
+template <int NC, int KSTEPS, bool A_SMEM, bool ISSUER, class ChunkOf, class Epi>
 __device__ __forceinline__ void layer_finish(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
   // The accumulator of chunk i+1 is fetched (tcgen05.ld, asynchronous) as soon as chunk i's registers are dead, so its
   // TMEM round trip and mbarrier wake-up hide behind chunk i's store / fence / barrier / MMA issue.
-  uint32_t v[32];
-  tmem_ld32(wait_chunk(cx), v);
+  if constexpr (ISSUER) {
 #pragma unroll
-  for (int i = 0; i < NC; ++i) {
-    tmem_ld_wait();
-    trace_mark(cx, 10 + i);
-    epi(i, v, [&]() { if (i + 1 < NC) tmem_ld32(wait_chunk(cx), v); });
-    trace_mark(cx, 20 + i);
-    tc_fence_before();
-    wg_barrier(cx.wg);
-    trace_mark(cx, 30 + i);
-    if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));
+    for (int i = 0; i < NC; ++i) {
+      step_done<true>(cx);   // wait until every epilogue warp has drained the slot and written its part of A'
+      if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM, true>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));
+    }
+  } else {
+    uint32_t v[32];
+    tmem_ld32(wait_chunk(cx), v);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      tmem_ld_wait();
+      trace_mark(cx, 10 + i);
+      epi(i, v, [&]() { if (i + 1 < NC) tmem_ld32(wait_chunk(cx), v); });
+      trace_mark(cx, 20 + i);
+      tc_fence_before();
+      step_done<false>(cx);   // arrive and move on: epilogue warps never wait for each other
+      if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM, false>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));   // (counter only)
+    }
   }
 }
-template <int NC, int KSTEPS, bool A_SMEM, class ChunkOf, class Epi>
+template <int NC, int KSTEPS, bool A_SMEM, bool ISSUER, class ChunkOf, class Epi>
 __device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
-  layer_begin<NC, KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of);
-  layer_finish<NC, KSTEPS, A_SMEM>(cx, a_base, w_smem, n_rows, chunk_of, epi);
+  layer_begin<NC, KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of);
+  layer_finish<NC, KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of, epi);
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -379,7 +398,8 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   const int tid = threadIdx.x;
   // warp-uniform quantities are broadcast from lane 0 so that ptxas keeps them in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  cx.wg = warp >> 3;
+  cx.issuer = warp >= 16;
+  cx.wg = cx.issuer ? warp - 16 : warp >> 3;
   cx.tid_wg = tid & 255;
   const int warp_in_wg = warp & 7;
   cx.warp_in_wg = warp_in_wg;
@@ -389,7 +409,7 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   cx.tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0) + (uint32_t)cx.wg * 256u;
   cx.lane_addr = cx.tmem + ((uint32_t)(quarter * 32) << 16);
   cx.full = s.bars + 1 + 2 * cx.wg;
-  cx.n_issued = cx.n_waited = 0;
+  cx.n_issued = cx.n_waited = cx.n_steps = 0;
   cx.trace = nullptr;
   return cx;
 }
@@ -472,6 +492,7 @@ __global__ void __launch_bounds__(256, 1) k0_project_kernel(const __grid_constan
 // =================================================================================================
 // CH = this thread's column half (compile-time so that every bias / weight index is an immediate
 // constant-bank operand instead of a per-thread LDC)
+template <bool ISSUER>
 __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;   // warp-uniform (broadcast from lane 0): constant-bank indices stay uniform-register loads
   const uint32_t wsm = smem_u32(smem);
@@ -490,7 +511,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
     trace_mark(cx, 1);
     // ---- stage A, first layer (hoisted): h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
-    {
+    if constexpr (!ISSUER) {
       const int iy = g.y.idx[jy], ix = g.x.idx[jx];
       const float rely = g.y.rel[jy], relx = g.x.rel[jx];
       const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
@@ -511,26 +532,26 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       }
       tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
       tmem_st_wait();
+      tc_fence_before();
     }
     trace_mark(cx, 2);
-    tc_fence_before();
-    wg_barrier(cx.wg);
+    step_done<ISSUER>(cx);
     trace_mark(cx, 3);
 
     // ---- feat_imnet hidden layers
-    run_layer<1, 4, false>(cx, cx.tmem + kColAin, wsm + k1F1, 64, [](int) { return 0; },
+    run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
-    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
     });
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
     auto f3_order = [](int i) { return i == 2 ? 0 : i + 1; };
-    layer_begin<3, 16, false>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order);
+    layer_begin<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order);
     // ---- stage B gather, placed after the composed layer's first MMAs are issued so its latency hides behind them:
     //      gB = bilinear(TB; query position) + cB + composed bias of F                  (:410-418)
     float gB[32];
-    {
+    if constexpr (!ISSUER) {
       const Taps tp = make_taps_tables(g, jy, jx);
       uint16_t wq[4];
 #pragma unroll
@@ -553,18 +574,19 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     }
 
     trace_mark(cx, 4);
-    layer_finish<3, 16, false>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
+    layer_finish<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
       if (i < 2) epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
       else epi_flow_first_layer(v, cx.lane_addr + kColAin + CH * 16, gB, pf);
     });
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
-    run_layer<1, 4, false>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
+    run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, p.c.l3_w + 64 * i + ch0, fl, pf); });
     // combine the two column halves and store
+    if constexpr (ISSUER) continue;
     const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
     if (CH == 1) part[cx.row] = mine;
     wg_barrier(cx.wg);
@@ -576,16 +598,17 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
   }
 }
 
-__global__ void __launch_bounds__(512, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
+__global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
   const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
   WgCtx cx = make_wg(s);
-  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && threadIdx.x < 512) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
   if (p.dephase_clk != 0 && cx.wg == (p.dephase_clk > 0 ? 1 : 0)) {   // > 0 delays WG1, < 0 delays WG0
     const long long t0 = clock64(), d = p.dephase_clk > 0 ? p.dephase_clk : -p.dephase_clk;
     while (clock64() - t0 < d) __nanosleep(200);
   }
-  k1_tile_loop(p, s, cx);
+  if (cx.issuer) k1_tile_loop<true>(p, s, cx);
+  else k1_tile_loop<false>(p, s, cx);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -705,6 +728,7 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
   __syncwarp();
 }
 
+template <bool ISSUER>
 __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
@@ -716,7 +740,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   const int ch0 = CH * 32;
 
   const long tile_first = (long)blockIdx.x * 2 + cx.wg;
-  if (tile_first < ntiles) k2_gather_taps(p, stg, tile_first, warp_in_wg, lane);
+  if (tile_first < ntiles && !ISSUER) k2_gather_taps(p, stg, tile_first, warp_in_wg, lane);
   for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
     bool valid;
@@ -724,7 +748,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
     trace_mark(cx, 1);
-    {  // L2 prefetch for this WG's NEXT tile: the lines a small flow would touch (own pixel, rows -1/0/+1).
+    if constexpr (!ISSUER) {  // L2 prefetch for this WG's NEXT tile: the lines a small flow would touch (own pixel, rows -1/0/+1).
        // Pure hint: a wrong guess costs nothing but the prefetch itself.
       bool vn;
       const long qn = k2_query(p, tile + (long)gridDim.x * 2, cx.row, vn);
@@ -737,27 +761,30 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
         if (CH == 0) prefetch_l2(reinterpret_cast<const float4*>(p.flow) + qn);
       }
     }
-    k2_gather_blend(p, a0, stg, warp_in_wg, lane);
+    if constexpr (!ISSUER) {
+      k2_gather_blend(p, a0, stg, warp_in_wg, lane);
+      fence_proxy_async_smem();
+      tc_fence_before();
+    }
     trace_mark(cx, 2);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    wg_barrier(cx.wg);
+    step_done<ISSUER>(cx);
     trace_mark(cx, 3);
 
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
-    run_layer<1, 4, true>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
+    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
-    run_layer<4, 4, false>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    layer_begin<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
+    layer_begin<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
     {  // footprints of this WG's next tile, computed while the first 256->256 chunk is on the tensor pipe
       const long tile_next = tile + (long)gridDim.x * 2;
-      if (tile_next < ntiles) k2_gather_taps(p, stg, tile_next, warp_in_wg, lane);
+      if (tile_next < ntiles && !ISSUER) k2_gather_taps(p, stg, tile_next, warp_in_wg, lane);
     }
-    layer_finish<4, 16, false>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
+    layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb, pf); });
+    if constexpr (ISSUER) continue;
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
     wg_barrier(cx.wg);
@@ -772,16 +799,17 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   }
 }
 
-__global__ void __launch_bounds__(512, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
+__global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
   WgCtx cx = make_wg(s);
-  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && threadIdx.x < 512) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
   if (p.dephase_clk != 0 && cx.wg == (p.dephase_clk > 0 ? 1 : 0)) {   // > 0 delays WG1, < 0 delays WG0
     const long long t0 = clock64(), d = p.dephase_clk > 0 ? p.dephase_clk : -p.dephase_clk;
     while (clock64() - t0 < d) __nanosleep(200);
   }
-  k2_tile_loop(p, s, cx);
+  if (cx.issuer) k2_tile_loop<true>(p, s, cx);
+  else k2_tile_loop<false>(p, s, cx);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -832,6 +860,13 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k0_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (getenv("STIF_DEBUG_ATTRS")) {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k1_stage_ab_kernel);
+    fprintf(stderr, "k1: regs %d maxThreads %d smem static %zu local %zu\n", a.numRegs, a.maxThreadsPerBlock, a.sharedSizeBytes, a.localSizeBytes);
+    cudaFuncGetAttributes(&a, k2_stage_cde_kernel);
+    fprintf(stderr, "k2: regs %d maxThreads %d smem static %zu local %zu\n", a.numRegs, a.maxThreadsPerBlock, a.sharedSizeBytes, a.localSizeBytes);
+  }
   if (e != cudaSuccess) {
     err = cudaGetErrorString(e);
     tc_weights_destroy(t);
@@ -940,7 +975,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.trace = trace_buffer();
     p.dephase_clk = dephase_clocks(1);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
-    k1_stage_ab_kernel<<<grid, 512, k1Smem, cx.stream>>>(p);
+    k1_stage_ab_kernel<<<grid, 576, k1Smem, cx.stream>>>(p);
     ++*cx.launch_counter;
     trace_dump("K1", cx.stream);
     return cudaGetLastError();
@@ -967,7 +1002,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.trace = trace_buffer();
   p.dephase_clk = dephase_clocks(2);
   if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
-  k2_stage_cde_kernel<<<grid, 512, k2Smem, cx.stream>>>(p);
+  k2_stage_cde_kernel<<<grid, 576, k2Smem, cx.stream>>>(p);
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
   return cudaGetLastError();
