@@ -328,9 +328,8 @@ __device__ __forceinline__ void epi_store_qtab(uint32_t (&v)[32], const float* _
   }
   next_ld();
   if (!valid) return;
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) d4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  stg256(dst, o);            // two full 32-byte sectors per thread
+  stg256(dst + 16, o + 8);
 }
 
 // f0 = sin(F + g) -> bf16 -> TMEM (g already holds bilinear(TB) + time constant + composed bias)
@@ -517,11 +516,13 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
       const uint4* ta = tab4 + (inb ? ((long)iy * g.W + ix) : 0) * 32 + CH * 4;
       uint32_t pk[16];
+      U8x32 ta2;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint4 v = __ldg(ta + j);
-        if (!inb) v = make_uint4(0, 0, 0, 0);
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+        if ((j & 1) == 0) ta2 = ldg256(ta + j);
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w4[e] = inb ? ta2.r[(j & 1) * 4 + e] : 0u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = ch0 + j * 8 + e * 2;
@@ -557,17 +558,16 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
 #pragma unroll
       for (int k = 0; k < 4; ++k) wq[k] = __half_as_ushort(__float2half_rn(tp.w[k]));
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gB[8 * j + e] = p.c.cB[ch0 + 8 * j + e] + p.c.f3_b[ch0 + 8 * j + e];
+        for (int e = 0; e < 16; ++e) gB[16 * j + e] = p.c.cB[ch0 + 16 * j + e] + p.c.f3_b[ch0 + 16 * j + e];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint4 v = __ldg(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + j);
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+          const U8x32 v = ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            gB[8 * j + 2 * e] = fma_f16((uint16_t)(w4[e] & 0xFFFF), wq[k], gB[8 * j + 2 * e]);
-            gB[8 * j + 2 * e + 1] = fma_f16((uint16_t)(w4[e] >> 16), wq[k], gB[8 * j + 2 * e + 1]);
+          for (int e = 0; e < 8; ++e) {
+            gB[16 * j + 2 * e] = fma_f16((uint16_t)(v.r[e] & 0xFFFF), wq[k], gB[16 * j + 2 * e]);
+            gB[16 * j + 2 * e + 1] = fma_f16((uint16_t)(v.r[e] >> 16), wq[k], gB[16 * j + 2 * e + 1]);
           }
         }
       }

@@ -56,6 +56,30 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gm
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// 256-bit global accesses (sm_100+: LDG.256 / STG.256): one instruction per full 32-byte sector
+struct alignas(32) U8x32 { uint32_t r[8]; };
+__device__ __forceinline__ U8x32 ldg256(const void* p) {
+  U8x32 a;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.r[0]), "=r"(a.r[1]), "=r"(a.r[2]), "=r"(a.r[3]), "=r"(a.r[4]), "=r"(a.r[5]), "=r"(a.r[6]), "=r"(a.r[7])
+               : "l"(p));
+  return a;
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* a) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]),
+               "r"(a[5]), "r"(a[6]), "r"(a[7])
+               : "memory");
+}
+// shared::cta -> global bulk store (TMA); completion tracked with bulk groups of the issuing thread
+__device__ __forceinline__ void bulk_store_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the issuing thread's bulk stores have finished READING shared memory (the buffer may be rewritten)
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have fully completed (global writes performed)
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // make generic-proxy smem writes visible to the async proxy (tcgen05.mma reads smem through it)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
