@@ -145,6 +145,12 @@ int stif_ensemble_weights(int H, int W, int HH, int WW, float* weights_host, siz
  * Returns STIF_ESTATE if no decode has run. */
 int stif_debug_last_flow(stif_decoder_t* dec, float* flow_host, size_t num_floats);
 
+/* Tuning / introspection of stif_decode_host's band-major pipeline (bf16 mode): the latent is uploaded in `bands` LR row
+ * bands (default 6) and stage C-E of a band trails stage A-B by `halo` HR rows (default 32, doubled by the library after a
+ * call in which a warp reached further; that call repeats stage C-E on the complete tables, so results never depend on
+ * these knobs).  Values <= 0 leave a knob unchanged; *respins (may be NULL) receives how many times a repeat was needed. */
+int stif_debug_host_pipeline(stif_decoder_t* dec, int bands, int halo, int64_t* respins);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t stif_launch_count(const stif_decoder_t* dec);
 

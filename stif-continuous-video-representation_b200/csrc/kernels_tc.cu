@@ -99,7 +99,7 @@ struct K2Params {
   int tiles_x;              // K2 tiles are 8 rows x 16 columns (2 x 4 warp patches of 4 x 4 queries): neighbouring
                             // queries of a warp share bilinear taps in x AND y, so the L1 / in-flight-miss merge removes
                             // most of the duplicate line requests of the gather
-  int band_lo, band_hi, band_mode;
+  int band_lo_off, band_hi_off;   // Q-table pixels [lo, hi) exist (stage A+B rows of this launch); taps outside raise *flag
   int* flag;
   long long* trace;
   int dephase_clk;
@@ -643,15 +643,17 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
     const float4 fl = __ldg(reinterpret_cast<const float4*>(p.flow) + q);
     float gy, gx;
     warp_position(g, jy, jx, which ? fl.z : fl.x, which ? fl.w : fl.y, gy, gx);   // (warplayer.py:25-39)
-    const Taps hr = make_taps(gy, gx, g.HH, g.WW);
-    const Taps lr = make_taps(gy, gx, g.H, g.W);
-    if (p.band_mode) {
+    Taps hr = make_taps(gy, gx, g.HH, g.WW);
+    Taps lr = make_taps(gy, gx, g.H, g.W);
+    // Row-band launches: rows outside [band_lo, band_hi) of the Q table (and the LR rows behind them) may not be
+    // written yet.  A tap that carries weight there is a halo violation (flagged; the host repeats the launch);
+    // a zero-weight tap is redirected to data that certainly exists (the query's own pixel / texel 0), because
+    // 0 x stale bits is not 0 when the bits are a NaN.  (Full-raster launches: the window is everything.)
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (hr.w[k] != 0.f) {
-          const int row = hr.off[k] / g.WW;
-          if (row < p.band_lo || row >= p.band_hi) atomicOr(p.flag, 1);
-        }
+    for (int k = 0; k < 4; ++k) {
+      if (hr.w[k] == 0.f) hr.off[k] = (int)q;
+      else if (hr.off[k] < p.band_lo_off || hr.off[k] >= p.band_hi_off) atomicOr(p.flag, 1);
+      if (lr.w[k] == 0.f) lr.off[k] = 0;
     }
     const uint32_t cb = which * 128u;
     uint4* dst = stg + qi * 6;
@@ -993,9 +995,8 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.row_begin = row_begin;
   p.row_end = row_end;
   p.tiles_x = (geo.WW + 15) / 16;
-  p.band_lo = k1_row_begin;
-  p.band_hi = k1_row_end;
-  p.band_mode = (k1_row_begin > 0 || k1_row_end < geo.HH) ? 1 : 0;
+  p.band_lo_off = k1_row_begin * geo.WW;
+  p.band_hi_off = k1_row_end * geo.WW;
   p.flag = ws.flag;
   const long ntiles = (long)p.tiles_x * ((row_end - row_begin + 7) / 8);
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);

@@ -91,6 +91,9 @@ struct stif_decoder {
   void* host_scratch = nullptr;
   size_t host_scratch_bytes = 0;
   cudaStream_t host_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
+  int host_bands = 6;        // LR row bands of the host pipeline
+  int host_halo = 32;        // HR rows by which K2 trails K1 in the banded host pipeline (doubles after a miss)
+  int64_t host_respins = 0;  // how often the speculation missed and K2 was repeated
 };
 
 namespace stif {
@@ -236,6 +239,145 @@ struct HostPipe {
   int bands;
 };
 
+// Number of timesteps whose Q table + flow stay resident at once in the banded host pipeline.
+constexpr int kHostGroup = 4;
+size_t host_group_extra_bytes(int HH, int WW, int T) {
+  const size_t Q = (size_t)HH * WW;
+  return (size_t)(std::min(T, kHostGroup) - 1) * (align256(Q * 128 * 2) + align256(Q * 4 * sizeof(float)));
+}
+
+// Band-major host pipeline (bf16 mode).  The latent arrives in LR row bands; everything downstream is stream-ordered
+// behind the band that makes it computable, so uploads, kernels and downloads of different bands overlap:
+//   band k:  H2D(k) -> K0(k) -> K1(t, HR rows [he[k-1], he[k]))  for every t of the group
+//                            -> K2(t, HR rows [ge[k-1], ge[k]))  -> D2H of those RGB rows
+// he[k] = first HR row whose nearest / bilinear LR footprint is not yet covered by bands 0..k (exact, from the axis
+// tables).  ge[k] = he[k] - halo is SPECULATIVE: stage D reads stage-A rows at flow-displaced positions, so K2 of a
+// band trails K1 by `halo` HR rows and raises the workspace flag when a warp reaches a row that is not there yet
+// (the same check stif_decode_rows uses).  If that ever happens the group's K2 launches are repeated on the complete
+// tables after the loop, and the handle doubles its halo for the following calls (flows of a video are consistent).
+// `workspace` must hold stif_workspace_bytes() + host_group_extra_bytes().
+int decode_host_banded(stif_decoder* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
+                       const float* times, int T, int mode, void* workspace, float* out, cudaStream_t stream, const HostPipe& hp) {
+  const Geometry* geo = nullptr;
+  if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo)) return rc;
+  const Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
+  LaunchCtx cx{stream, &d->launches, d->num_sms};
+  const size_t Q = (size_t)HH * WW, plane = (size_t)H * W;
+  const int G = std::min(T, kHostGroup);
+  const size_t qtab_b = align256(Q * 128 * 2), flow_b = align256(Q * 4 * sizeof(float));
+  auto slab_ws = [&](int g) {   // timestep g of the group: its own Q table and flow
+    Workspace w = ws;
+    if (g > 0) {
+      char* extra = (char*)workspace + ws.total_bytes + (size_t)(g - 1) * (qtab_b + flow_b);
+      w.qtab = extra;
+      w.flow = (float*)(extra + qtab_b);
+    }
+    return w;
+  };
+  const int nbands = std::max(1, std::min(hp.bands, H));
+  const int halo = std::min(HH, std::max(1, d->host_halo));
+  HostAxis ay;
+  build_axis(H, HH, ay);
+  std::vector<int> he(nbands, HH), ge(nbands, HH);
+  for (int k = 0; k + 1 < nbands; ++k) {
+    const int r1 = (int)((long)H * (k + 1) / nbands);
+    int h = k ? he[k - 1] : 0;
+    while (h < HH && ay.idx[h] < r1 && ay.b0[h] + 1 < r1) ++h;
+    he[k] = h;
+    ge[k] = std::max(k ? ge[k - 1] : 0, (h - halo) & ~7);
+  }
+  std::vector<cudaEvent_t> used_events;
+  auto chain = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {   // `to` waits for what `from` holds now
+    cudaEvent_t ev = take_event(d);
+    used_events.push_back(ev);
+    cudaError_t e = cudaEventRecord(ev, from);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
+  };
+  auto k2_rows = [&](int b, int c, const Workspace& w, int g0, int g1, int k1_hi) -> int {   // K2 + download of RGB rows [g0,g1)
+    if (g1 <= g0) return STIF_OK;
+    float* out_slab = out + ((size_t)c * B + b) * 3 * Q;
+    {
+      ScopedSpan sp(d, stream, 2);
+      cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, w, times[(size_t)c * B + b], g0, g1, 0, k1_hi, out_slab, 2);
+      if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+    }
+    CUDA_OR_RETURN(chain(stream, hp.d2h));
+    CUDA_OR_RETURN(cudaMemcpy2DAsync(hp.out_host + ((size_t)c * B + b) * 3 * Q + (size_t)g0 * WW, Q * 4, out_slab + (size_t)g0 * WW, Q * 4,
+                                     (size_t)(g1 - g0) * WW * 4, 3, cudaMemcpyDeviceToHost, hp.d2h));
+    return STIF_OK;
+  };
+  CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
+  // all uploads are queued up front (they depend on nothing); one event per (item, band)
+  std::vector<cudaEvent_t> landed((size_t)B * nbands);
+  for (int b = 0; b < B; ++b)
+    for (int k = 0; k < nbands; ++k) {
+      const int r0 = (int)((long)H * k / nbands), r1 = (int)((long)H * (k + 1) / nbands);
+      const size_t off = (size_t)b * 192 * plane + (size_t)r0 * W, offf = (size_t)b * 6 * plane + (size_t)r0 * W;
+      const size_t width = (size_t)(r1 - r0) * W * sizeof(float);
+      CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)latent + off, plane * 4, hp.latent_host + off, plane * 4, width, 192,
+                                       cudaMemcpyHostToDevice, hp.h2d));
+      CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)frames + offf, plane * 4, hp.frames_host + offf, plane * 4, width, 6,
+                                       cudaMemcpyHostToDevice, hp.h2d));
+      cudaEvent_t ev = take_event(d);
+      used_events.push_back(ev);
+      CUDA_OR_RETURN(cudaEventRecord(ev, hp.h2d));
+      landed[(size_t)b * nbands + k] = ev;
+    }
+  for (int b = 0; b < B; ++b) {
+    const float* lat_b = latent + (size_t)b * 192 * plane;
+    const float* fr_b = frames + (size_t)b * 6 * plane;
+    for (int k = 0; k < nbands; ++k) {
+      const int r0 = (int)((long)H * k / nbands), r1 = (int)((long)H * (k + 1) / nbands);
+      CUDA_OR_RETURN(cudaStreamWaitEvent(stream, landed[(size_t)b * nbands + k], 0));
+      {
+        ScopedSpan sp(d, stream, 0);
+        CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
+      }
+      const int h0 = k ? he[k - 1] : 0, h1 = he[k];
+      for (int g = 0; g < G && h1 > h0; ++g) {
+        ScopedSpan sp(d, stream, 1);
+        cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, slab_ws(g), times[(size_t)g * B + b], 0, HH, h0, h1, out, 1);
+        if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+      }
+      for (int g = 0; g < G; ++g)
+        if (int rc = k2_rows(b, g, slab_ws(g), k ? ge[k - 1] : 0, ge[k], h1)) return rc;
+    }
+    // speculation check for this item (the flag is only read here, after the tables are complete)
+    int flag = 0;
+    if (nbands > 1) {
+      CUDA_OR_RETURN(cudaMemcpyAsync(&flag, ws.flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      CUDA_OR_RETURN(cudaStreamSynchronize(stream));
+    }
+    if (flag) {
+      d->host_halo = std::min(HH, 2 * halo);
+      ++d->host_respins;
+      CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
+      for (int g = 0; g < G; ++g)
+        if (int rc = k2_rows(b, g, slab_ws(g), 0, HH, HH)) return rc;
+    }
+    // timesteps beyond the resident group: one slab at a time on complete tables; the download of slab c overlaps
+    // slab c+1, and the last slab is decoded in row bands so that only its last band's download is exposed
+    for (int c = G; c < T; ++c) {
+      {
+        ScopedSpan sp(d, stream, 1);
+        cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, ws, times[(size_t)c * B + b], 0, HH, 0, HH, out, 1);
+        if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+      }
+      const int parts = (c == T - 1 && b == B - 1) ? nbands : 1;
+      for (int k = 0; k < parts; ++k)
+        if (int rc = k2_rows(b, c, ws, (int)((long)HH * k / parts) & ~7, k + 1 == parts ? HH : (int)((long)HH * (k + 1) / parts) & ~7, HH))
+          return rc;
+    }
+  }
+  CUDA_OR_RETURN(cudaStreamSynchronize(hp.d2h));
+  CUDA_OR_RETURN(cudaStreamSynchronize(stream));
+  for (auto e : used_events) d->event_pool.push_back(e);
+  const Workspace last = slab_ws(T <= G ? T - 1 : 0);
+  d->last_flow = last.flow;
+  d->last_flow_floats = Q * 4;
+  return STIF_OK;
+}
+
 int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
                 const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
                 size_t workspace_bytes, float* out, cudaStream_t stream, bool check_band, const HostPipe* hp = nullptr) {
@@ -256,6 +398,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (workspace_bytes < need)
     return set_error(STIF_ENOMEM, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
   CUDA_OR_RETURN(cudaSetDevice(d->device));
+  if (hp && prec == STIF_MODE_BF16) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
   const Geometry* geo = nullptr;
   if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo)) return rc;
   Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
@@ -266,21 +409,6 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   std::vector<cudaEvent_t> used_events;
   const int nbands = hp ? std::max(1, std::min(hp->bands, H)) : 1;
   const size_t plane = (size_t)H * W;
-  // Host pipeline, bf16 mode: stage A+B of the first timestep is launched per row band right behind the
-  // band's projection, so the upload of band k+1 overlaps K0/K1 of band k.  band_hr_end[k] = first HR row
-  // whose nearest / bilinear LR footprint (rows idx, b0, b0+1) is not yet covered by bands 0..k.
-  const bool band_k1 = hp && prec == STIF_MODE_BF16 && nbands > 1 && row_begin == 0 && row_end == HH;
-  std::vector<int> band_hr_end(nbands, HH);
-  if (band_k1) {
-    HostAxis ay;
-    build_axis(H, HH, ay);
-    for (int k = 0; k + 1 < nbands; ++k) {
-      const int r1 = (int)((long)H * (k + 1) / nbands);
-      int h = 0;
-      while (h < HH && ay.idx[h] < r1 && ay.b0[h] + 1 < r1) ++h;
-      band_hr_end[k] = h;
-    }
-  }
   for (int b = 0; b < B; ++b) {
     const float* lat_b = latent + (size_t)b * 192 * plane;
     const float* fr_b = frames + (size_t)b * 6 * plane;
@@ -300,14 +428,6 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
       ScopedSpan sp(d, stream, 0);
       if (prec == STIF_MODE_BF16) CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
       else if (k == nbands - 1) CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false));
-      if (band_k1) {
-        const int h0 = k == 0 ? 0 : band_hr_end[k - 1], h1 = band_hr_end[k];
-        if (h1 > h0) {
-          ScopedSpan sp1(d, stream, 1);
-          cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, ws, times[b], 0, HH, h0, h1, out + (size_t)b * 3 * Q, 1);
-          if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
-        }
-      }
     }
     for (int c = 0; c < T; ++c) {
       const float t = times[(size_t)c * B + b];
@@ -320,7 +440,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
         continue;
       }
-      for (int stage = (band_k1 && c == 0) ? 2 : 1; stage <= 2; ++stage) {
+      for (int stage = 1; stage <= 2; ++stage) {
         ScopedSpan sp(d, stream, stage);
         cudaError_t e = (prec == STIF_MODE_FP32)
                             ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
@@ -469,7 +589,7 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   }
   const size_t lat_b = align256((size_t)B * 192 * H * W * 4), fr_b = align256((size_t)B * 6 * H * W * 4);
   const size_t out_b = align256((size_t)T * B * 3 * HH * WW * 4);
-  const size_t ws_b = stif_workspace_bytes(B, H, W, HH, WW, T, mode);
+  const size_t ws_b = stif_workspace_bytes(B, H, W, HH, WW, T, mode) + host_group_extra_bytes(HH, WW, T);
   const size_t total = lat_b + fr_b + out_b + ws_b;
   if (d->host_scratch_bytes < total) {
     if (d->host_scratch) cudaFree(d->host_scratch);
@@ -484,8 +604,16 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   float* out = (float*)(base + lat_b + fr_b);
   void* ws = base + lat_b + fr_b + out_b;
   cudaStream_t s = d->host_stream;
-  HostPipe hp{latent_host, frames_host, out_host, d->h2d_stream, d->d2h_stream, 6};
+  HostPipe hp{latent_host, frames_host, out_host, d->h2d_stream, d->d2h_stream, d->host_bands};
   return decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false, &hp);
+}
+
+int stif_debug_host_pipeline(stif_decoder_t* d, int bands, int halo, int64_t* respins) {
+  if (!d) return set_error(STIF_EINVAL, "null decoder");
+  if (bands > 0) d->host_bands = bands;
+  if (halo > 0) d->host_halo = halo;
+  if (respins) *respins = d->host_respins;
+  return STIF_OK;
 }
 
 int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* rel, float* base) {

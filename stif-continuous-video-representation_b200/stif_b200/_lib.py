@@ -22,7 +22,7 @@ STIF_ABI_VERSION = 1
 EXPORTS = [
     "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
     "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_axis_tables",
-    "stif_ensemble_weights", "stif_debug_last_flow", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
+    "stif_ensemble_weights", "stif_debug_last_flow", "stif_debug_host_pipeline", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
 ]
 
 
@@ -52,6 +52,7 @@ def _load():
     lib.stif_axis_tables.argtypes = [C.c_int, C.c_int, fp, ip, fp, fp]
     lib.stif_ensemble_weights.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t]
     lib.stif_debug_last_flow.argtypes = [vp, fp, C.c_size_t]
+    lib.stif_debug_host_pipeline.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.stif_launch_count.argtypes = [vp]
     lib.stif_launch_count.restype = C.c_int64
     lib.stif_profile_enable.argtypes = [vp, C.c_int]

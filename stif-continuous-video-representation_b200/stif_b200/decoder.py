@@ -258,6 +258,13 @@ class STIFQueryDecoder(torch.nn.Module):
         check(lib.stif_profile_read(self._handle, ms, cnt))
         return {"ms": list(ms), "count": list(cnt)}
 
+    def host_pipeline(self, bands: int = 0, halo: int = 0) -> int:
+        """Tune ``decode_host``'s band-major pipeline (``stif_debug_host_pipeline``; values <= 0 keep the current setting)
+        and return how many calls so far had to repeat stage C-E because a warp out-ran the speculative halo."""
+        n = C.c_int64(0)
+        check(lib.stif_debug_host_pipeline(self._handle, int(bands), int(halo), C.byref(n)))
+        return int(n.value)
+
     @property
     def launch_count(self) -> int:
         return int(lib.stif_launch_count(self._handle))

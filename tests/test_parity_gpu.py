@@ -219,3 +219,35 @@ def test_host_entry_point(decoders):
     out = dec.decode_host(lat, fr, [0.0, 0.375], None).numpy()
     g = np.load(os.path.join(GOLD, "case_x4_init.npz"))["rgb"]
     assert np.abs(out - g).max() <= 1e-4
+
+
+@pytest.mark.parametrize("stress,halo,expect_respin", [(False, 32, False), (True, 1, True)])
+def test_host_pipeline_matches_device_path(stif, stress, halo, expect_respin):
+    """stif_decode_host's band-major pipeline (bf16): uploads, kernels and downloads of different row bands overlap and
+    stage C-E trails stage A-B by a speculative halo.  Whatever the knobs, the result must be BIT-identical to the
+    device-buffer path (same kernels, same per-query arithmetic); with +-20 px stress flows and a 1-row halo the
+    speculation must miss, be detected and be repaired.  T = 6 also covers the timesteps beyond the resident group."""
+    dec = stif.STIFQueryDecoder(0, mode="bf16")
+    dec.load_weights(synth.make_weights(1, stress))
+    lat, fr = synth.make_inputs(5, 1, 96, 40, 1.0 if stress else 0.05)
+    times = [0.0, 0.2, 0.4, 0.6, 0.8, 1.0]
+    ref = _run(dec, lat, fr, times, (384, 163))
+    before = dec.host_pipeline(bands=6, halo=halo)
+    out = dec.decode_host(lat, fr, times, (384, 163)).numpy()
+    respins = dec.host_pipeline() - before
+    assert np.isfinite(out).all()
+    assert np.array_equal(out, ref)
+    assert (respins > 0) == expect_respin, respins
+    # a second call after a miss runs with the doubled halo and still agrees
+    out2 = dec.decode_host(lat, fr, times, (384, 163)).numpy()
+    assert np.array_equal(out2, ref)
+
+
+def test_host_pipeline_batch_of_two(stif):
+    dec = stif.STIFQueryDecoder(0, mode="bf16")
+    dec.load_weights(synth.make_weights(2, True))
+    lat, fr = synth.make_inputs(6, 2, 24, 20, 0.3)
+    times = [[0.25, 0.75], [0.5, 0.1]]
+    ref = _run(dec, lat, fr, times, (61, 77))
+    out = dec.decode_host(lat, fr, _times(times), (61, 77)).numpy()
+    assert np.array_equal(out, ref)
