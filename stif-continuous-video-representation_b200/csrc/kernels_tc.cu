@@ -357,9 +357,17 @@ struct CtaSetup {
   uint32_t tmem_base;
 };
 
+// Programmatic dependent launch: every kernel lets its successor in the stream be scheduled at once (its CTAs take SMs
+// as ours retire and run their prologue -- barrier init, TMEM allocation, the weight image's TMA load -- early), and
+// itself waits for its predecessor's results only after its own prologue.  All grids are persistent (<= one CTA per
+// SM, all resident from the start), so an early successor can never starve its predecessor of SMs.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ CtaSetup cta_prologue(uint32_t bars_off, uint32_t w_off, const uint8_t* wimg, uint32_t wbytes,
                                                  uint32_t tmem_cols) {
   CtaSetup s;
+  pdl_launch_dependents();
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // SW128 operands assume a 1024-byte aligned window
   s.bars = reinterpret_cast<uint64_t*>(smem + bars_off);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bars_off + 64);
@@ -383,6 +391,7 @@ __device__ __forceinline__ CtaSetup cta_prologue(uint32_t bars_off, uint32_t w_o
     }
   }
   s.tmem_base = *tmem_slot;
+  pdl_wait_for_predecessor();   // nothing above reads or writes data another kernel produces
   return s;
 }
 
@@ -822,6 +831,21 @@ void fill_from(float* dst, const std::vector<float>& src, size_t n) { std::copy(
 // =================================================================================================
 // host side
 // =================================================================================================
+template <class P>
+cudaError_t launch_pdl(void (*kern)(const P), int grid, int block, size_t smem_bytes, cudaStream_t stream, const P& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 struct TcWeights {
   uint8_t* d_k0 = nullptr;
   uint8_t* d_k1 = nullptr;
@@ -911,7 +935,7 @@ cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const fl
   p.m_begin = (long)row_begin * W;
   p.m_end = (long)row_end * W;
   const long ntiles = (p.m_end - p.m_begin + kTile - 1) / kTile;
-  k0_project_kernel<<<(int)std::min<long>(cx.num_sms, ntiles), 256, k0Smem, cx.stream>>>(p);
+  if (cudaError_t e = launch_pdl(k0_project_kernel, (int)std::min<long>(cx.num_sms, ntiles), 256, k0Smem, cx.stream, p)) return e;
   ++*cx.launch_counter;
   return cudaGetLastError();
 }
@@ -977,7 +1001,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.trace = trace_buffer();
     p.dephase_clk = dephase_clocks(1);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
-    k1_stage_ab_kernel<<<grid, 576, k1Smem, cx.stream>>>(p);
+    if (cudaError_t e = launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)) return e;
     ++*cx.launch_counter;
     trace_dump("K1", cx.stream);
     return cudaGetLastError();
@@ -1003,7 +1027,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.trace = trace_buffer();
   p.dephase_clk = dephase_clocks(2);
   if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
-  k2_stage_cde_kernel<<<grid, 576, k2Smem, cx.stream>>>(p);
+  if (cudaError_t e = launch_pdl(k2_stage_cde_kernel, grid, 576, k2Smem, cx.stream, p)) return e;
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
   return cudaGetLastError();

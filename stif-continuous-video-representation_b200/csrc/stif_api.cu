@@ -8,6 +8,7 @@
 #include <array>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -92,6 +93,7 @@ struct stif_decoder {
   size_t host_scratch_bytes = 0;
   cudaStream_t host_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
   int host_bands = 6;        // LR row bands of the host pipeline
+  bool host_bands_forced = false;   // set through stif_debug_host_pipeline: keep the band count even for tiny rasters
   int host_halo = 32;        // HR rows by which K2 trails K1 in the banded host pipeline (doubles after a miss)
   int64_t host_respins = 0;  // how often the speculation missed and K2 was repeated
 };
@@ -274,17 +276,40 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
     }
     return w;
   };
-  const int nbands = std::max(1, std::min(hp.bands, H));
   const int halo = std::min(HH, std::max(1, d->host_halo));
   HostAxis ay;
   build_axis(H, HH, ay);
-  std::vector<int> he(nbands, HH), ge(nbands, HH);
-  for (int k = 0; k + 1 < nbands; ++k) {
-    const int r1 = (int)((long)H * (k + 1) / nbands);
-    int h = k ? he[k - 1] : 0;
-    while (h < HH && ay.idx[h] < r1 && ay.b0[h] + 1 < r1) ++h;
-    he[k] = h;
-    ge[k] = std::max(k ? ge[k - 1] : 0, (h - halo) & ~7);
+  // Band plan.  The kernels are persistent with static tile assignment, so a launch of n tiles costs ceil(n / slots)
+  // tile times (slots = 2 tiles per SM): band heights are chosen so that each launch fills just under a whole number
+  // of waves.  he[k] / ge[k] = end of band k in HR rows for stage A+B / stage C-E, lr_end[k] = LR rows the band needs.
+  const long slots = 2L * d->num_sms;
+  auto k1_tiles = [&](int rows) { return ((long)rows * WW + 127) / 128; };
+  auto k2_tiles = [&](int rows) { return (long)((rows + 7) / 8) * ((WW + 15) / 16); };
+  auto wave_aligned = [&](int target, int step, auto tiles_of) {
+    int best = std::max(step, target / step * step);
+    double best_eff = 0.0;
+    for (int r = std::max(step, (int)(0.8 * target) / step * step); r <= (int)(1.05 * target); r += step) {
+      const double w = (double)tiles_of(r) / (double)slots, eff = w / std::ceil(w);
+      if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && std::abs(r - target) < std::abs(best - target))) { best = r; best_eff = eff; }
+    }
+    return best;
+  };
+  int nbands = std::max(1, std::min(hp.bands, H));
+  if (!d->host_bands_forced && k1_tiles(HH) < 2 * slots * nbands) nbands = 1;   // small rasters: a band would not even fill two waves
+  std::vector<int> he(nbands, HH), ge(nbands, HH), lr_end(nbands, H);
+  if (nbands > 1) {
+    // the first band is half height: the pipeline starts (and the first rows leave) after a short upload
+    // (heights are multiples of 8 rows so that stage C-E, whose tiles are 8 rows high, keeps pace with stage A+B)
+    auto both_tiles = [&](int rows) { return std::max(k1_tiles(rows), k2_tiles(rows)); };
+    const int first = wave_aligned(HH / (2 * nbands - 1), 8, both_tiles);
+    const int r1 = wave_aligned((HH - first) / (nbands - 1), 8, both_tiles);
+    for (int k = 0; k + 1 < nbands; ++k) {
+      he[k] = std::min(HH, first + k * r1);
+      ge[k] = std::max(k ? ge[k - 1] : 0, (he[k] - halo) & ~7);
+      const int last = he[k] - 1;   // LR rows the nearest / bilinear footprints of HR rows < he[k] touch (tables are monotone)
+      lr_end[k] = std::min(H, std::max(ay.idx[last], ay.b0[last] + 1) + 1);
+      if (k && lr_end[k] < lr_end[k - 1]) lr_end[k] = lr_end[k - 1];
+    }
   }
   std::vector<cudaEvent_t> used_events;
   auto chain = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {   // `to` waits for what `from` holds now
@@ -293,31 +318,50 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
     cudaError_t e = cudaEventRecord(ev, from);
     return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
   };
-  auto k2_rows = [&](int b, int c, const Workspace& w, int g0, int g1, int k1_hi) -> int {   // K2 + download of RGB rows [g0,g1)
+  // K2 of RGB rows [g0,g1) for timesteps [c0,c1) back to back (nothing between the launches, so each one's prologue
+  // overlaps its predecessor's tail), then one event and the downloads of those rows
+  auto k2_rows = [&](int b, int c0, int c1, bool resident, int g0, int g1, int k1_hi) -> int {
     if (g1 <= g0) return STIF_OK;
-    float* out_slab = out + ((size_t)c * B + b) * 3 * Q;
-    {
+    for (int c = c0; c < c1; ++c) {
       ScopedSpan sp(d, stream, 2);
-      cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, w, times[(size_t)c * B + b], g0, g1, 0, k1_hi, out_slab, 2);
+      cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, resident ? slab_ws(c) : ws, times[(size_t)c * B + b], g0, g1, 0, k1_hi,
+                                     out + ((size_t)c * B + b) * 3 * Q, 2);
       if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
     }
     CUDA_OR_RETURN(chain(stream, hp.d2h));
-    CUDA_OR_RETURN(cudaMemcpy2DAsync(hp.out_host + ((size_t)c * B + b) * 3 * Q + (size_t)g0 * WW, Q * 4, out_slab + (size_t)g0 * WW, Q * 4,
-                                     (size_t)(g1 - g0) * WW * 4, 3, cudaMemcpyDeviceToHost, hp.d2h));
+    for (int c = c0; c < c1; ++c) {
+      const size_t o = ((size_t)c * B + b) * 3 * Q + (size_t)g0 * WW;
+      CUDA_OR_RETURN(cudaMemcpy2DAsync(hp.out_host + o, Q * 4, out + o, Q * 4, (size_t)(g1 - g0) * WW * 4, 3, cudaMemcpyDeviceToHost, hp.d2h));
+    }
     return STIF_OK;
   };
+  // STIF_HOST_TIMELINE=1: print when each band's upload / stage A+B / stage C-E / download finished (ms since the
+  // first copy was queued).  Debug aid; the extra event records sit between kernels.
+  static const bool timeline = getenv("STIF_HOST_TIMELINE") != nullptr;
+  struct Mark { cudaEvent_t ev; const char* what; int b, k; };
+  std::vector<Mark> marks;
+  auto mark = [&](cudaStream_t st, const char* what, int b, int k) {
+    if (!timeline) return;
+    cudaEvent_t ev = take_event(d);
+    used_events.push_back(ev);
+    cudaEventRecord(ev, st);
+    marks.push_back({ev, what, b, k});
+  };
+  mark(hp.h2d, "start", 0, 0);
   CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
   // all uploads are queued up front (they depend on nothing); one event per (item, band)
   std::vector<cudaEvent_t> landed((size_t)B * nbands);
   for (int b = 0; b < B; ++b)
     for (int k = 0; k < nbands; ++k) {
-      const int r0 = (int)((long)H * k / nbands), r1 = (int)((long)H * (k + 1) / nbands);
+      const int r0 = k ? lr_end[k - 1] : 0, r1 = lr_end[k];
       const size_t off = (size_t)b * 192 * plane + (size_t)r0 * W, offf = (size_t)b * 6 * plane + (size_t)r0 * W;
       const size_t width = (size_t)(r1 - r0) * W * sizeof(float);
-      CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)latent + off, plane * 4, hp.latent_host + off, plane * 4, width, 192,
-                                       cudaMemcpyHostToDevice, hp.h2d));
-      CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)frames + offf, plane * 4, hp.frames_host + offf, plane * 4, width, 6,
-                                       cudaMemcpyHostToDevice, hp.h2d));
+      if (r1 > r0) {
+        CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)latent + off, plane * 4, hp.latent_host + off, plane * 4, width, 192,
+                                         cudaMemcpyHostToDevice, hp.h2d));
+        CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)frames + offf, plane * 4, hp.frames_host + offf, plane * 4, width, 6,
+                                         cudaMemcpyHostToDevice, hp.h2d));
+      }
       cudaEvent_t ev = take_event(d);
       used_events.push_back(ev);
       CUDA_OR_RETURN(cudaEventRecord(ev, hp.h2d));
@@ -327,20 +371,23 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
     const float* lat_b = latent + (size_t)b * 192 * plane;
     const float* fr_b = frames + (size_t)b * 6 * plane;
     for (int k = 0; k < nbands; ++k) {
-      const int r0 = (int)((long)H * k / nbands), r1 = (int)((long)H * (k + 1) / nbands);
+      const int r0 = k ? lr_end[k - 1] : 0, r1 = lr_end[k];
       CUDA_OR_RETURN(cudaStreamWaitEvent(stream, landed[(size_t)b * nbands + k], 0));
-      {
+      if (r1 > r0) {
         ScopedSpan sp(d, stream, 0);
         CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
       }
+      mark(stream, "K0", b, k);
       const int h0 = k ? he[k - 1] : 0, h1 = he[k];
       for (int g = 0; g < G && h1 > h0; ++g) {
         ScopedSpan sp(d, stream, 1);
         cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, slab_ws(g), times[(size_t)g * B + b], 0, HH, h0, h1, out, 1);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
-      for (int g = 0; g < G; ++g)
-        if (int rc = k2_rows(b, g, slab_ws(g), k ? ge[k - 1] : 0, ge[k], h1)) return rc;
+      mark(stream, "K1", b, k);
+      if (int rc = k2_rows(b, 0, G, true, k ? ge[k - 1] : 0, ge[k], h1)) return rc;
+      mark(stream, "K2", b, k);
+      mark(hp.d2h, "D2H", b, k);
     }
     // speculation check for this item (the flag is only read here, after the tables are complete)
     int flag = 0;
@@ -352,8 +399,7 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
       d->host_halo = std::min(HH, 2 * halo);
       ++d->host_respins;
       CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
-      for (int g = 0; g < G; ++g)
-        if (int rc = k2_rows(b, g, slab_ws(g), 0, HH, HH)) return rc;
+      if (int rc = k2_rows(b, 0, G, true, 0, HH, HH)) return rc;
     }
     // timesteps beyond the resident group: one slab at a time on complete tables; the download of slab c overlaps
     // slab c+1, and the last slab is decoded in row bands so that only its last band's download is exposed
@@ -365,12 +411,27 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
       }
       const int parts = (c == T - 1 && b == B - 1) ? nbands : 1;
       for (int k = 0; k < parts; ++k)
-        if (int rc = k2_rows(b, c, ws, (int)((long)HH * k / parts) & ~7, k + 1 == parts ? HH : (int)((long)HH * (k + 1) / parts) & ~7, HH))
+        if (int rc = k2_rows(b, c, c + 1, false, (int)((long)HH * k / parts) & ~7,
+                             k + 1 == parts ? HH : (int)((long)HH * (k + 1) / parts) & ~7, HH))
           return rc;
     }
   }
   CUDA_OR_RETURN(cudaStreamSynchronize(hp.d2h));
   CUDA_OR_RETURN(cudaStreamSynchronize(stream));
+  if (timeline) {
+    for (int b = 0; b < B; ++b)
+      for (int k = 0; k < nbands; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, marks[0].ev, landed[(size_t)b * nbands + k]);
+        fprintf(stderr, "[stif host] b%d band %d: H2D %.3f", b, k, ms);
+        for (size_t i = 1; i < marks.size(); ++i)
+          if (marks[i].b == b && marks[i].k == k) {
+            cudaEventElapsedTime(&ms, marks[0].ev, marks[i].ev);
+            fprintf(stderr, "  %s %.3f", marks[i].what, ms);
+          }
+        fprintf(stderr, "   (HR rows A+B < %d, C-E < %d)\n", he[k], ge[k]);
+      }
+  }
   for (auto e : used_events) d->event_pool.push_back(e);
   const Workspace last = slab_ws(T <= G ? T - 1 : 0);
   d->last_flow = last.flow;
@@ -610,7 +671,7 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
 
 int stif_debug_host_pipeline(stif_decoder_t* d, int bands, int halo, int64_t* respins) {
   if (!d) return set_error(STIF_EINVAL, "null decoder");
-  if (bands > 0) d->host_bands = bands;
+  if (bands > 0) { d->host_bands = bands; d->host_bands_forced = true; }
   if (halo > 0) d->host_halo = halo;
   if (respins) *respins = d->host_respins;
   return STIF_OK;
