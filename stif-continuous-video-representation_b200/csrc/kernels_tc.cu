@@ -425,67 +425,80 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
 // =================================================================================================
 // K0: latent projection  tab[HW,256] (fp16) = [latent(192) ; frames(6)]^T  W_tab^T      (bf16 MMA)
 // =================================================================================================
-__global__ void __launch_bounds__(256, 1) k0_project_kernel(const __grid_constant__ K0Params p) {
+// 512 threads: thread = (texel row, quarter of the channel groups).  The fp32 planes of the NEXT tile are fetched into
+// registers (up to 54 loads per thread = the whole 101 KB tile in flight per SM) before the current tile's MMA is
+// awaited and its accumulator is written out, so HBM latency hides behind the epilogue instead of serialising with it.
+__global__ void __launch_bounds__(512, 1) k0_project_kernel(const __grid_constant__ K0Params p) {
   const CtaSetup s = cta_prologue(k0Bars, k0B, p.wimg, k0WBytes, 256);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = tid & 127, khalf = tid >> 7;
+  const int row = tid & 127, part = tid >> 7;
   const long ntiles = (p.m_end - p.m_begin + kTile - 1) / kTile;
   const uint32_t a_sm = smem_u32(smem + k0A), b_sm = smem_u32(smem + k0B);
   // K index 200..207 (group 25) is padding: zero it once (B is zero there too, but 0 * garbage could be NaN)
-  if (khalf == 1) *reinterpret_cast<uint4*>(smem + k0A + 3 * 16384 + sw128_offset(row, 8)) = make_uint4(0, 0, 0, 0);
+  if (part == 1) *reinterpret_cast<uint4*>(smem + k0A + 3 * 16384 + sw128_offset(row, 8)) = make_uint4(0, 0, 0, 0);
+  // channel groups of 8: this thread owns g8 = part + 4 i, i = 0..5 (latent) and, for part 0, group 24 (the 6 frame planes)
+  float v[48], f[6];
+  auto fetch = [&](long tile) {
+    const long m = min(p.m_begin + tile * kTile + row, p.m_end - 1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[8 * i + e] = __ldg(p.latent + (long)((part + 4 * i) * 8 + e) * p.HW + m);
+    if (part == 0) {
+#pragma unroll
+      for (int e = 0; e < 6; ++e) f[e] = __ldg(p.frames + (long)e * p.HW + m);
+    }
+  };
+  if ((long)blockIdx.x < ntiles) fetch(blockIdx.x);
   mbar_wait_or_trap(&s.bars[0], 0);
   uint32_t phase = 0;
   for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long m = min(p.m_begin + tile * kTile + row, p.m_end - 1);
-    // ---- A tile: thread = (texel row, half of the channel groups); 8 channels -> one 16-byte smem chunk
-#pragma unroll 1
-    for (int gg = 0; gg < 13; ++gg) {
-      const int g8 = khalf * 13 + gg;      // channel group: channels [8 g8, 8 g8 + 8)
-      if (g8 >= 25) break;
-      float v[8];
-      if (g8 < 24) {
+    // ---- A tile: 8 channels -> one 16-byte chunk of the SW128 image
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(p.latent + (long)(g8 * 8 + e) * p.HW + m);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 6; ++e) v[e] = __ldg(p.frames + (long)e * p.HW + m);
-        v[6] = v[7] = 0.f;
-      }
-      const uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-      *reinterpret_cast<uint4*>(smem + k0A + (g8 >> 3) * 16384 + sw128_offset(row, (g8 & 7) * 8)) = o;
+    for (int i = 0; i < 6; ++i) {
+      const int g8 = part + 4 * i;
+      *reinterpret_cast<uint4*>(smem + k0A + (g8 >> 3) * 16384 + sw128_offset(row, (g8 & 7) * 8)) =
+          make_uint4(pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]), pack_bf16x2(v[8 * i + 4], v[8 * i + 5]),
+                     pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
     }
+    if (part == 0)
+      *reinterpret_cast<uint4*>(smem + k0A + 3 * 16384 + sw128_offset(row, 0)) =
+          make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), 0u);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
-      const uint32_t idesc = make_idesc_bf16(128, 256);
-      for (int j = 0; j < 13; ++j)    // K = 208 = 13 x 16
-        umma_ss(s.tmem_base, make_desc_sw128(a_sm + (j >> 2) * 16384) + 2 * (j & 3), make_desc_sw128(b_sm + (j >> 2) * 32768) + 2 * (j & 3),
-                idesc, j > 0);
-      umma_commit(&s.bars[1]);
+      if (elect_one()) {
+        const uint32_t idesc = make_idesc_bf16(128, 256);
+#pragma unroll
+        for (int j = 0; j < 13; ++j)    // K = 208 = 13 x 16
+          umma_ss(s.tmem_base, make_desc_sw128(a_sm + (j >> 2) * 16384) + 2 * (j & 3), make_desc_sw128(b_sm + (j >> 2) * 32768) + 2 * (j & 3),
+                  idesc, j > 0);
+        umma_commit(&s.bars[1]);
+      }
+      __syncwarp();
     }
+    if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);   // in flight across the MMA wait and the epilogue
     mbar_wait_or_trap(&s.bars[1], phase);
     phase ^= 1;
     tc_fence_after();
-    // ---- epilogue: warp = (lane quarter, column half); thread = one texel row, 128 channels
+    // ---- epilogue: warp = (lane quarter, column quarter); thread = one texel row, 64 channels = one 128-byte line
     {
-      const int quarter = warp & 3, colhalf = warp >> 2;
+      const int quarter = warp & 3, cq = warp >> 2;
       const long texel = p.m_begin + tile * kTile + quarter * 32 + lane;
-      const uint32_t src = s.tmem_base + ((uint32_t)(quarter * 32) << 16) + colhalf * 128;
+      const uint32_t src = s.tmem_base + ((uint32_t)(quarter * 32) << 16) + cq * 64;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(src + c * 32, v);
+      for (int c = 0; c < 2; ++c) {
+        uint32_t a[32], o[16];
+        tmem_ld32(src + c * 32, a);
         tmem_ld_wait();
-        if (texel < p.m_end) {
-          uint4* dst = reinterpret_cast<uint4*>(p.tab + texel * 256 + colhalf * 128 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack_half2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                                pack_half2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                                pack_half2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                                pack_half2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+        for (int j = 0; j < 16; ++j) o[j] = pack_half2(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+        if (texel < p.m_end) {
+          __half* dst = p.tab + texel * 256 + cq * 64 + c * 32;
+          stg256(dst, o);
+          stg256(dst + 16, o + 8);
         }
       }
     }
@@ -935,7 +948,7 @@ cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const fl
   p.m_begin = (long)row_begin * W;
   p.m_end = (long)row_end * W;
   const long ntiles = (p.m_end - p.m_begin + kTile - 1) / kTile;
-  if (cudaError_t e = launch_pdl(k0_project_kernel, (int)std::min<long>(cx.num_sms, ntiles), 256, k0Smem, cx.stream, p)) return e;
+  if (cudaError_t e = launch_pdl(k0_project_kernel, (int)std::min<long>(cx.num_sms, ntiles), 512, k0Smem, cx.stream, p)) return e;
   ++*cx.launch_counter;
   return cudaGetLastError();
 }
