@@ -122,7 +122,8 @@ struct WgCtx {
   uint64_t* full;      // two mbarriers: accumulator slot s is complete
   uint32_t n_issued, n_waited, n_steps;
   int wg, tid_wg, warp_in_wg, row, colhalf;
-  bool issuer;         // this warp only issues the WG's MMAs (warps 16, 17); the other 8 warps of the WG only run epilogues
+  int slot;            // logical warp slot: 0..15 epilogue warps (WG0 then WG1), 16/17 the issuers (trace rows, per-warp smem)
+  bool issuer;         // this warp only issues the WG's MMAs (warps 0, 1); the other 8 warps of the WG only run epilogues
   long long* trace;    // this thread's trace cursor (null unless tracing)
 };
 
@@ -174,6 +175,7 @@ template <int KSTEPS, bool A_SMEM, bool ISSUER>
 __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, int chunk) {
   const uint32_t slot = cx.n_issued & 1;
   if (ISSUER) {
+    trace_mark(cx, 40);
     tc_fence_after();
     const uint32_t idesc = make_idesc_bf16(128, 64);
     const uint32_t d = cx.tmem + kColD + slot * 64;
@@ -190,6 +192,7 @@ __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t
       umma_commit(&cx.full[slot]);
     }
     __syncwarp();
+    trace_mark(cx, 41);
   }
   ++cx.n_issued;
 }
@@ -406,13 +409,18 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   const int tid = threadIdx.x;
   // warp-uniform quantities are broadcast from lane 0 so that ptxas keeps them in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  cx.issuer = warp >= 16;
-  cx.wg = cx.issuer ? warp - 16 : warp >> 3;
-  cx.tid_wg = tid & 255;
-  const int warp_in_wg = warp & 7;
+  // Warps 0 and 1 are the MMA issuers, warps 2..17 the epilogue warps.  The issuers must be the OLDEST warps of their
+  // scheduler: with the issuers last (warps 16, 17) the greedy-then-oldest pick starved them behind four always-ready
+  // epilogue warps -- ~2400 clocks between "accumulator slot free" and the next chunk's first tcgen05.mma.
+  cx.issuer = warp < 2;
+  const int ew = warp - 2;                   // epilogue warp 0..15
+  cx.wg = cx.issuer ? warp : ew >> 3;
+  const int warp_in_wg = ew & 7;
+  cx.slot = cx.issuer ? 16 + warp : ew;
+  cx.tid_wg = warp_in_wg * 32 + (tid & 31);
   cx.warp_in_wg = warp_in_wg;
-  const int quarter = warp_in_wg & 3;        // == (global warp id) % 4 : the TMEM lane quarter this warp may access
-  cx.colhalf = warp_in_wg >> 2;
+  const int quarter = warp & 3;              // the TMEM lane quarter this warp may access = (warp id) % 4
+  cx.colhalf = warp_in_wg >> 2;              // epilogue warps w and w+4 of a WG share a quarter and split the columns
   cx.row = quarter * 32 + (tid & 31);
   cx.tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0) + (uint32_t)cx.wg * 256u;
   cx.lane_addr = cx.tmem + ((uint32_t)(quarter * 32) << 16);
@@ -623,7 +631,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
 __global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
   const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
   WgCtx cx = make_wg(s);
-  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && threadIdx.x < 512) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
   if (p.dephase_clk != 0 && cx.wg == (p.dephase_clk > 0 ? 1 : 0)) {   // > 0 delays WG1, < 0 delays WG0
     const long long t0 = clock64(), d = p.dephase_clk > 0 ? p.dephase_clk : -p.dephase_clk;
@@ -756,7 +764,7 @@ template <bool ISSUER>
 __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warp_in_wg = warp & 7;
+  const int lane = threadIdx.x & 31, warp = cx.slot & 15, warp_in_wg = cx.warp_in_wg;
   uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
   uint4* stg = reinterpret_cast<uint4*>(smem + k2Taps + warp * 1536);
   float4* part = reinterpret_cast<float4*>(a0);   // partial-sum exchange reuses the WG's A tile (dead after the first MMA)
@@ -826,7 +834,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
 __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
   WgCtx cx = make_wg(s);
-  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && threadIdx.x < 512) cx.trace = p.trace + (threadIdx.x >> 5) * 4096;
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
   if (p.dephase_clk != 0 && cx.wg == (p.dephase_clk > 0 ? 1 : 0)) {   // > 0 delays WG1, < 0 delays WG0
     const long long t0 = clock64(), d = p.dephase_clk > 0 ? p.dephase_clk : -p.dephase_clk;
@@ -961,7 +969,7 @@ long long* trace_buffer() {
   if (!init) {
     init = true;
     if (getenv("STIF_TRACE")) {
-      cudaMalloc(&buf, 16 * 4096 * sizeof(long long));
+      cudaMalloc(&buf, 18 * 4096 * sizeof(long long));
     }
   }
   return buf;
@@ -979,11 +987,11 @@ void trace_dump(const char* kernel, cudaStream_t stream) {
   long long* buf = trace_buffer();
   if (!buf) return;
   cudaStreamSynchronize(stream);
-  std::vector<long long> h(16 * 4096);
+  std::vector<long long> h(18 * 4096);
   cudaMemcpy(h.data(), buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   FILE* f = fopen(getenv("STIF_TRACE"), "a");
   if (!f) return;
-  for (int w = 0; w < 16; ++w) {
+  for (int w = 0; w < 18; ++w) {
     fprintf(f, "%s warp %d:", kernel, w);
     for (int i = 0; i + 1 < 4096 && h[w * 4096 + i] != 0; i += 2) fprintf(f, " %lld:%lld", h[w * 4096 + i], h[w * 4096 + i + 1]);
     fprintf(f, "\n");
@@ -1013,7 +1021,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
     p.trace = trace_buffer();
     p.dephase_clk = dephase_clocks(1);
-    if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
+    if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
     if (cudaError_t e = launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)) return e;
     ++*cx.launch_counter;
     trace_dump("K1", cx.stream);
@@ -1039,7 +1047,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
   p.trace = trace_buffer();
   p.dephase_clk = dephase_clocks(2);
-  if (p.trace) cudaMemsetAsync(p.trace, 0, 16 * 4096 * sizeof(long long), cx.stream);
+  if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
   if (cudaError_t e = launch_pdl(k2_stage_cde_kernel, grid, 576, k2Smem, cx.stream, p)) return e;
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
