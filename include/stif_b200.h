@@ -51,6 +51,10 @@ extern "C" {
 #define STIF_MODE_FP32      1  /* fp32 FMA-pipe kernels; RGB within 1e-4 of the reference                           */
 /* flags OR-ed into `mode` */
 #define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085) */
+#define STIF_FLAG_OUT_U8         0x200  /* write what the reference's caller makes of the result (custom_video_test.py:102):
+                                         * `(img.clamp(0,1).permute(1,2,0) * 255).astype(uint8)` -- uint8 [T,B,HH,WW,3],
+                                         * fp32 clamp / multiply, truncation.  The `out` pointer is then a uint8_t buffer and
+                                         * device<->host output traffic drops 4x. */
 
 /* number of weight tensors the decoder consumes (state-dict order, see stif_load_weights) */
 #define STIF_NUM_WEIGHT_TENSORS 26
@@ -91,7 +95,8 @@ size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode
  *   times_host  [T,B] fp32         (times[c][b]; the reference passes [1,1] or [B,1] tensors per c)
  *   (HH,WW)     output raster size; the reference's `scale` argument IS this size
  *               (Sakuya_arch_test.py:368-371); the x4 default is (4H,4W)
- *   out_rgb_dev [T,B,3,HH,WW] fp32, unclamped (== torch.stack(preds))
+ *   out_rgb_dev [T,B,3,HH,WW] fp32, unclamped (== torch.stack(preds));
+ *               with STIF_FLAG_OUT_U8: uint8 [T,B,HH,WW,3] (see the flag)
  * With STIF_FLAG_LOCAL_ENSEMBLE (STIF_MODE_FP32 only in this build) the result is
  * decoding_localensemble's: B must be 1 as in the reference, out is [T,1,3,HH,WW]. */
 int stif_decode(stif_decoder_t* dec,
@@ -99,7 +104,7 @@ int stif_decode(stif_decoder_t* dec,
                 int B, int H, int W, int HH, int WW,
                 const float* times_host, int T, int mode,
                 void* workspace_dev, size_t workspace_bytes,
-                float* out_rgb_dev, void* stream);
+                void* out_rgb_dev, void* stream);
 
 /* Same as stif_decode but the query raster is restricted to rows [row_begin,row_end) of every
  * (t,b) slab -- the unit the multi-GPU launcher shards when slabs < GPUs.  Stage A/B of the
@@ -114,7 +119,7 @@ int stif_decode_rows(stif_decoder_t* dec,
                      const float* times_host, int T, int mode,
                      int row_begin, int row_end, int halo,
                      void* workspace_dev, size_t workspace_bytes,
-                     float* out_rgb_dev, void* stream);
+                     void* out_rgb_dev, void* stream);
 
 /* End-to-end convenience for FFI callers that hold HOST buffers: allocates device memory
  * internally (cached on the handle), copies latent/frames host->device, decodes, copies RGB
@@ -123,7 +128,7 @@ int stif_decode_host(stif_decoder_t* dec,
                      const float* latent_host, const float* frames_host,
                      int B, int H, int W, int HH, int WW,
                      const float* times_host, int T, int mode,
-                     float* out_rgb_host);
+                     void* out_rgb_host);
 
 /* ---- introspection used by the parity tests (same device functions as the decode path) ---- */
 

@@ -214,6 +214,39 @@ Vec64 time_constant(const std::vector<float>& wt, const std::vector<float>& b, f
 }  // namespace
 
 // tab[texel, 0:256] = w_tab [256,198] . [latent(192); frames(6)][texel]      (t-independent)
+// Output conversion of the reference's caller (custom_video_test.py:102): `(img.clamp(0,1) * 255).astype(np.uint8)` on the
+// HWC-permuted frame, i.e. fp32 clamp, fp32 multiply, truncation.  planar [3, Q] fp32 -> interleaved [Q, 3] uint8, rows
+// [row_begin, row_end) of the raster.  Four pixels per thread: 3 coalesced plane reads, one 12-byte run written as words.
+__global__ void rgb_to_u8_hwc_kernel(const float* __restrict__ rgb, uint8_t* __restrict__ out, long Q, long q_begin, long q_end) {
+  const long q0 = (q_begin & ~3L) + ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (q0 >= q_end) return;
+  uint8_t v[12];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long q = min(max(q0 + i, q_begin), q_end - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[3 * i + c] = (uint8_t)(fminf(fmaxf(__ldg(rgb + c * Q + q), 0.f), 1.f) * 255.f);
+  }
+  if (q0 >= q_begin && q0 + 3 < q_end) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + q0 * 3);   // q0 % 4 == 0 -> 12-byte aligned run, 4-byte aligned words
+#pragma unroll
+    for (int w = 0; w < 3; ++w) o[w] = v[4 * w] | (v[4 * w + 1] << 8) | (v[4 * w + 2] << 16) | ((uint32_t)v[4 * w + 3] << 24);
+  } else {
+    for (int i = 0; i < 4; ++i)
+      if (q0 + i >= q_begin && q0 + i < q_end)
+        for (int c = 0; c < 3; ++c) out[(q0 + i) * 3 + c] = v[3 * i + c];
+  }
+}
+
+cudaError_t rgb_to_u8_hwc(const LaunchCtx& cx, const float* rgb_planar, uint8_t* out_hwc, int HH, int WW, int row_begin, int row_end) {
+  const long Q = (long)HH * WW, q_begin = (long)row_begin * WW, q_end = (long)row_end * WW;
+  if (q_end <= q_begin) return cudaSuccess;
+  const long groups = (q_end - (q_begin & ~3L) + 3) / 4;
+  rgb_to_u8_hwc_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, cx.stream>>>(rgb_planar, out_hwc, Q, q_begin, q_end);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
 cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
                            int H, int W, void* tab, bool tab_half) {
   GemmArgs g{};

@@ -115,6 +115,7 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
   ws.qtab = take(Q * 128 * esz);
   ws.flow = (float*)take(Q * 4 * sizeof(float));
   ws.flag = (int*)take(256);
+  if (mode & STIF_FLAG_OUT_U8) ws.rgb32 = (float*)take(Q * 3 * sizeof(float));
   if (fp32) {
     ws.chunk = std::min<size_t>(Q, (size_t)1 << 18);
     ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
@@ -236,7 +237,8 @@ struct ScopedSpan {  // brackets one kernel group with events when profiling is 
 struct HostPipe {
   const float* latent_host;
   const float* frames_host;
-  float* out_host;
+  void* out_host;            // fp32 [T,B,3,HH,WW], or uint8 [T,B,HH,WW,3] with STIF_FLAG_OUT_U8
+  uint8_t* out_u8_dev;       // device copy of the uint8 result (STIF_FLAG_OUT_U8), else null
   cudaStream_t h2d, d2h;
   int bands;
 };
@@ -328,10 +330,20 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
                                      out + ((size_t)c * B + b) * 3 * Q, 2);
       if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
     }
+    if (hp.out_u8_dev)
+      for (int c = c0; c < c1; ++c) {
+        const size_t slab = ((size_t)c * B + b) * 3 * Q;
+        CUDA_OR_RETURN(rgb_to_u8_hwc(cx, out + slab, hp.out_u8_dev + slab, HH, WW, g0, g1));
+      }
     CUDA_OR_RETURN(chain(stream, hp.d2h));
     for (int c = c0; c < c1; ++c) {
-      const size_t o = ((size_t)c * B + b) * 3 * Q + (size_t)g0 * WW;
-      CUDA_OR_RETURN(cudaMemcpy2DAsync(hp.out_host + o, Q * 4, out + o, Q * 4, (size_t)(g1 - g0) * WW * 4, 3, cudaMemcpyDeviceToHost, hp.d2h));
+      const size_t slab = ((size_t)c * B + b) * 3 * Q, o = slab + (size_t)g0 * WW;
+      if (hp.out_u8_dev)   // HWC rows are contiguous
+        CUDA_OR_RETURN(cudaMemcpyAsync((uint8_t*)hp.out_host + slab + (size_t)g0 * WW * 3, hp.out_u8_dev + slab + (size_t)g0 * WW * 3,
+                                       (size_t)(g1 - g0) * WW * 3, cudaMemcpyDeviceToHost, hp.d2h));
+      else
+        CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)hp.out_host + o, Q * 4, out + o, Q * 4, (size_t)(g1 - g0) * WW * 4, 3, cudaMemcpyDeviceToHost,
+                                         hp.d2h));
     }
     return STIF_OK;
   };
@@ -441,14 +453,15 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
 
 int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
                 const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
-                size_t workspace_bytes, float* out, cudaStream_t stream, bool check_band, const HostPipe* hp = nullptr) {
+                size_t workspace_bytes, void* out_any, cudaStream_t stream, bool check_band, const HostPipe* hp = nullptr) {
+  float* out = (float*)out_any;   // fp32 [T,B,3,HH,WW], or with STIF_FLAG_OUT_U8 uint8 [T,B,HH,WW,3] (see out_u8 below)
   if (!d) return set_error(STIF_EINVAL, "null decoder");
   if (!d->weights_loaded) return set_error(STIF_ESTATE, "stif_load_weights has not been called");
   if (!latent || !frames || !times || !out || !workspace) return set_error(STIF_EINVAL, "null buffer");
   if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
   const int prec = mode & 0xFF;
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
-  const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0;
+  const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0, u8 = (mode & STIF_FLAG_OUT_U8) != 0;
   if (ensemble && prec != STIF_MODE_FP32)
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE is only available with STIF_MODE_FP32 in this build");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
@@ -459,7 +472,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (workspace_bytes < need)
     return set_error(STIF_ENOMEM, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
   CUDA_OR_RETURN(cudaSetDevice(d->device));
-  if (hp && prec == STIF_MODE_BF16) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
+  if (hp && prec == STIF_MODE_BF16 && !ensemble) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
   const Geometry* geo = nullptr;
   if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo)) return rc;
   Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
@@ -492,29 +505,33 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
     }
     for (int c = 0; c < T; ++c) {
       const float t = times[(size_t)c * B + b];
-      float* out_slab = out + ((size_t)c * B + b) * 3 * Q;
+      uint8_t* out_u8 = u8 ? (uint8_t*)out_any + ((size_t)c * B + b) * 3 * Q : nullptr;
+      float* out_slab = u8 ? ws.rgb32 : out + ((size_t)c * B + b) * 3 * Q;   // uint8 output: decode into the staging slab
       if (ensemble) {
         DeviceGeometry* dg = nullptr;
         if (int rc = get_ensemble_geometry(d, H, W, HH, WW, &dg)) return rc;
         ScopedSpan sp(d, stream, 1);
         cudaError_t e = decode_slab_fp32_ensemble(cx, d->w32, d->hw, dg->geo_pass, dg->ens_y, dg->ens_x, ws, t, out_slab);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
-        continue;
       }
-      for (int stage = 1; stage <= 2; ++stage) {
+      for (int stage = 1; stage <= 2 && !ensemble; ++stage) {
         ScopedSpan sp(d, stream, stage);
         cudaError_t e = (prec == STIF_MODE_FP32)
                             ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
                             : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
+      if (u8) CUDA_OR_RETURN(rgb_to_u8_hwc(cx, ws.rgb32, out_u8, HH, WW, row_begin, row_end));
       if (hp) {   // download this slab while the next one is decoded
         cudaEvent_t ev = take_event(d);
         used_events.push_back(ev);
         CUDA_OR_RETURN(cudaEventRecord(ev, stream));
         CUDA_OR_RETURN(cudaStreamWaitEvent(hp->d2h, ev, 0));
-        CUDA_OR_RETURN(cudaMemcpyAsync(hp->out_host + ((size_t)c * B + b) * 3 * Q, out_slab, 3 * Q * sizeof(float),
-                                       cudaMemcpyDeviceToHost, hp->d2h));
+        if (u8)
+          CUDA_OR_RETURN(cudaMemcpyAsync((uint8_t*)hp->out_host + ((size_t)c * B + b) * 3 * Q, out_u8, 3 * Q, cudaMemcpyDeviceToHost, hp->d2h));
+        else
+          CUDA_OR_RETURN(cudaMemcpyAsync((float*)hp->out_host + ((size_t)c * B + b) * 3 * Q, out_slab, 3 * Q * sizeof(float),
+                                         cudaMemcpyDeviceToHost, hp->d2h));
       }
     }
   }
@@ -625,20 +642,20 @@ size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode
 }
 
 int stif_decode(stif_decoder_t* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
-                const float* times, int T, int mode, void* workspace, size_t workspace_bytes, float* out, void* stream) {
+                const float* times, int T, int mode, void* workspace, size_t workspace_bytes, void* out, void* stream) {
   return decode_impl(d, latent, frames, B, H, W, HH, WW, times, T, mode, 0, HH, 0, workspace, workspace_bytes, out,
                      (cudaStream_t)stream, false);
 }
 
 int stif_decode_rows(stif_decoder_t* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
                      const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
-                     size_t workspace_bytes, float* out, void* stream) {
+                     size_t workspace_bytes, void* out, void* stream) {
   return decode_impl(d, latent, frames, B, H, W, HH, WW, times, T, mode, row_begin, row_end, halo, workspace, workspace_bytes,
                      out, (cudaStream_t)stream, true);
 }
 
 int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* frames_host, int B, int H, int W, int HH,
-                     int WW, const float* times, int T, int mode, float* out_host) {
+                     int WW, const float* times, int T, int mode, void* out_host) {
   if (!d) return set_error(STIF_EINVAL, "null decoder");
   if (!latent_host || !frames_host || !out_host) return set_error(STIF_EINVAL, "null buffer");
   if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
@@ -651,7 +668,8 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   const size_t lat_b = align256((size_t)B * 192 * H * W * 4), fr_b = align256((size_t)B * 6 * H * W * 4);
   const size_t out_b = align256((size_t)T * B * 3 * HH * WW * 4);
   const size_t ws_b = stif_workspace_bytes(B, H, W, HH, WW, T, mode) + host_group_extra_bytes(HH, WW, T);
-  const size_t total = lat_b + fr_b + out_b + ws_b;
+  const size_t out8_b = (mode & STIF_FLAG_OUT_U8) ? align256((size_t)T * B * 3 * HH * WW) : 0;
+  const size_t total = lat_b + fr_b + out_b + ws_b + out8_b;
   if (d->host_scratch_bytes < total) {
     if (d->host_scratch) cudaFree(d->host_scratch);
     d->host_scratch = nullptr;
@@ -665,7 +683,8 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   float* out = (float*)(base + lat_b + fr_b);
   void* ws = base + lat_b + fr_b + out_b;
   cudaStream_t s = d->host_stream;
-  HostPipe hp{latent_host, frames_host, out_host, d->h2d_stream, d->d2h_stream, d->host_bands};
+  HostPipe hp{latent_host, frames_host, out_host, out8_b ? (uint8_t*)base + lat_b + fr_b + out_b + ws_b : nullptr, d->h2d_stream, d->d2h_stream,
+              d->host_bands};
   return decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false, &hp);
 }
 

@@ -73,6 +73,7 @@ struct Workspace {
   float* ftab;    // local-ensemble mode: F = 30 Wl0[:, :64] HRfeat for the whole slab [HH*WW,64]
   float* pred;    // local-ensemble mode: one pass's prediction [3,HH*WW]
   int* flag;      // device int: row-band halo violation flag
+  float* rgb32;   // STIF_FLAG_OUT_U8: fp32 staging of one slab [3,HH*WW] ahead of the uint8 conversion
   size_t chunk;   // queries per activation chunk (FP32 mode)
   size_t total_bytes;
 };
@@ -86,6 +87,8 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
                              int k1_row_end, float* out_rgb /* [3,HH,WW] */, int stage /* 1 = K1 (A+B), 2 = K2 (C+D+E) */);
 // decoding_localensemble (Sakuya_arch_test.py:962-1085): 4 shifted passes blended by swapped areas.  geo_pass[k] carries the
 // shifted axis tables of pass k (loop order (vx,vy) = (-1,-1),(-1,1),(1,-1),(1,1)); ens_y/ens_x = tables for sign -1, +1.
+// custom_video_test.py:102 output conversion: planar fp32 [3,HH*WW] -> uint8 HWC, rows [row_begin,row_end)
+cudaError_t rgb_to_u8_hwc(const LaunchCtx& cx, const float* rgb_planar, uint8_t* out_hwc, int HH, int WW, int row_begin, int row_end);
 cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw,
                                       const Geometry geo_pass[4], const AxisTables ens_y[2], const AxisTables ens_x[2],
                                       const Workspace& ws, float t, float* out_rgb);

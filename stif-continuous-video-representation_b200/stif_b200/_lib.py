@@ -15,6 +15,7 @@ STIF_OK = 0
 STIF_MODE_BF16 = 0
 STIF_MODE_FP32 = 1
 STIF_FLAG_LOCAL_ENSEMBLE = 0x100
+STIF_FLAG_OUT_U8 = 0x200
 STIF_NUM_WEIGHT_TENSORS = 26
 STIF_ABI_VERSION = 1
 

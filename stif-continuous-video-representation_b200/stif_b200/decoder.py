@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import STIF_FLAG_LOCAL_ENSEMBLE, STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
+from ._lib import STIF_FLAG_LOCAL_ENSEMBLE, STIF_FLAG_OUT_U8, STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
 
 _MODES = {"bf16": STIF_MODE_BF16, "fp32": STIF_MODE_FP32}
 
@@ -148,20 +148,22 @@ class STIFQueryDecoder(torch.nn.Module):
 
     def decode_stacked(self, latent, frames, times, scale=None, mode: str | None = None,
                        rows: tuple[int, int] | None = None, halo: int = 0,
-                       out: torch.Tensor | None = None, local_ensemble: bool = False) -> torch.Tensor:
-        """Decode to one ``[T,B,3,HH,WW]`` tensor.  ``rows=(r0,r1)`` restricts the call to a row band
-        (``stif_decode_rows``), used by the sharding launcher."""
+                       out: torch.Tensor | None = None, local_ensemble: bool = False, uint8: bool = False) -> torch.Tensor:
+        """Decode to one ``[T,B,3,HH,WW]`` fp32 tensor.  ``rows=(r0,r1)`` restricts the call to a row band
+        (``stif_decode_rows``), used by the sharding launcher.  ``uint8=True`` returns what the reference's caller
+        saves (``custom_video_test.py:102``): ``(clamp(0,1) * 255).astype(uint8)`` as ``[T,B,HH,WW,3]``."""
         if not self._loaded:
             raise StifError("load_weights() has not been called")
         latent, frames, B, H, W, HH, WW = self._prep(latent, frames, scale)
         tm = _times_matrix(times, B)
         T = tm.shape[0]
-        m = _MODES[mode or self.mode] | (STIF_FLAG_LOCAL_ENSEMBLE if local_ensemble else 0)
+        m = _MODES[mode or self.mode] | (STIF_FLAG_LOCAL_ENSEMBLE if local_ensemble else 0) | (STIF_FLAG_OUT_U8 if uint8 else 0)
         ws = self._workspace_for(B, H, W, HH, WW, T, m)
+        shape, dtype = ((T, B, HH, WW, 3), torch.uint8) if uint8 else ((T, B, 3, HH, WW), torch.float32)
         if out is None:
-            out = torch.empty((T, B, 3, HH, WW), dtype=torch.float32, device=self.device)
-        elif tuple(out.shape) != (T, B, 3, HH, WW) or out.dtype != torch.float32 or not out.is_contiguous():
-            raise ValueError("out must be a contiguous fp32 [T,B,3,HH,WW] tensor")
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous {dtype} {list(shape)} tensor")
         stream = torch.cuda.current_stream(self.device).cuda_stream
         fp = tm.ctypes.data_as(C.POINTER(C.c_float))
         with torch.cuda.device(self.device):
@@ -186,8 +188,9 @@ class STIFQueryDecoder(torch.nn.Module):
         return self.decode_stacked(latent, frames, list(times), scale, mode="fp32", local_ensemble=True)[:, 0]
 
     def decode_host(self, latent: np.ndarray | torch.Tensor, frames, times, scale=None, mode: str | None = None,
-                    out: torch.Tensor | None = None) -> torch.Tensor:
-        """End-to-end call on HOST buffers (``stif_decode_host``): H2D copy, decode, D2H copy, sync."""
+                    out: torch.Tensor | None = None, uint8: bool = False) -> torch.Tensor:
+        """End-to-end call on HOST buffers (``stif_decode_host``): H2D copy, decode, D2H copy, sync.
+        ``uint8=True``: ``[T,B,HH,WW,3]`` uint8 frames as in ``decode_stacked`` (a quarter of the download)."""
         if not self._loaded:
             raise StifError("load_weights() has not been called")
         lat = torch.as_tensor(latent, dtype=torch.float32).contiguous()
@@ -198,9 +201,12 @@ class STIFQueryDecoder(torch.nn.Module):
         HH, WW = (4 * H, 4 * W) if scale is None else (int(scale[0]), int(scale[1]))
         tm = _times_matrix(times, B)
         T = tm.shape[0]
+        shape, dtype = ((T, B, HH, WW, 3), torch.uint8) if uint8 else ((T, B, 3, HH, WW), torch.float32)
         if out is None:
-            out = torch.empty((T, B, 3, HH, WW), dtype=torch.float32)
-        m = _MODES[mode or self.mode]
+            out = torch.empty(shape, dtype=dtype)
+        elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or out.device.type != "cpu":
+            raise ValueError(f"out must be a contiguous host {dtype} {list(shape)} tensor")
+        m = _MODES[mode or self.mode] | (STIF_FLAG_OUT_U8 if uint8 else 0)
         check(lib.stif_decode_host(self._handle, lat.data_ptr(), fr.data_ptr(), B, H, W, HH, WW,
                                    tm.ctypes.data_as(C.POINTER(C.c_float)), T, m, out.data_ptr()))
         return out

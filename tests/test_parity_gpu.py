@@ -251,3 +251,42 @@ def test_host_pipeline_batch_of_two(stif):
     ref = _run(dec, lat, fr, times, (61, 77))
     out = dec.decode_host(lat, fr, _times(times), (61, 77)).numpy()
     assert np.array_equal(out, ref)
+
+
+def _to_u8_like_reference(rgb):
+    """custom_video_test.py:102: (img.clamp(0,1).permute(1,2,0) * 255).numpy().astype(np.uint8), per (t, b) frame."""
+    x = torch.from_numpy(rgb).clamp(0.0, 1.0).permute(0, 1, 3, 4, 2) * 255
+    return np.ascontiguousarray(x.numpy().astype(np.uint8))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_uint8_output_flag(mode, decoders):
+    """STIF_FLAG_OUT_U8 = the conversion the reference's caller applies before saving a frame.  Bit-exact against that
+    conversion of the library's own fp32 result (device and host entry points, odd sizes, row bands), and within
+    tolerance*255 + 1 code values of the converted reference fixture."""
+    cfg = CASES["down_stress"]
+    lat, fr = synth.make_inputs(cfg["iseed"], cfg["B"], cfg["H"], cfg["W"], cfg["latent_std"])
+    dec = decoders(cfg["wseed"], cfg["stress"], mode)
+    # offset + gain so that the clamp bites on both sides
+    rgb = _run(dec, lat, fr, cfg["times"], cfg["scale"])
+    want = _to_u8_like_reference(rgb)
+    L, F = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    got = dec.decode_stacked(L, F, _times(cfg["times"]), cfg["scale"], uint8=True).cpu().numpy()
+    assert got.dtype == np.uint8 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert np.array_equal(dec.decode_host(lat, fr, _times(cfg["times"]), cfg["scale"], uint8=True).numpy(), want)
+    band = torch.zeros_like(torch.from_numpy(want)).cuda()
+    dec.decode_stacked(L, F, _times(cfg["times"]), cfg["scale"], rows=(3, 9), halo=13, out=band, uint8=True)
+    assert np.array_equal(band.cpu().numpy()[:, :, 3:9], want[:, :, 3:9]) and not band.cpu().numpy()[:, :, 9:].any()
+    ref = _to_u8_like_reference(np.load(os.path.join(GOLD, "case_down_stress.npz"))["rgb"])
+    assert np.abs(got.astype(np.int32) - ref.astype(np.int32)).max() <= int(TOL[mode] * 255) + 1
+
+
+def test_uint8_host_pipeline_banded(stif):
+    dec = stif.STIFQueryDecoder(0, mode="bf16")
+    dec.load_weights(synth.make_weights(1, True))
+    lat, fr = synth.make_inputs(5, 1, 96, 40, 0.05)
+    times = [0.0, 0.3, 0.6, 0.9, 1.0]
+    want = _to_u8_like_reference(_run(dec, lat, fr, times, (384, 163)))
+    dec.host_pipeline(bands=5, halo=16)
+    assert np.array_equal(dec.decode_host(lat, fr, times, (384, 163), uint8=True).numpy(), want)
