@@ -52,10 +52,18 @@ constexpr uint32_t kW64x64 = 64 * 64 * 2, kW256x64 = 256 * 64 * 2, kW192x256 = 1
 // K1: F1 | F2 | F3(composed 192x256) | L1 | L2 | partial-sum exchange
 constexpr uint32_t k1F1 = 0, k1F2 = k1F1 + kW64x64, k1F3 = k1F2 + kW256x64, k1L1 = k1F3 + kW192x256,
                    k1L2 = k1L1 + kW64x64, k1WBytes = k1L2 + kW256x64;
-constexpr uint32_t k1Part = k1WBytes, k1Bars = k1Part + 2 * 128 * 16, k1Smem = k1Bars + 128;
-// K2: E1 | E2 | E3 | A0[2 WGs] | tap staging [16 warps x 1536 B] (reused for the partial-sum exchange)
+// The fp32 output layers (256 -> 4 flow, 256 -> 3 RGB) are read once per (thread, column) on the FMA pipe.  From shared
+// memory that is one broadcast LDS.128 per four weights; from the constant bank it is a uniform load (LDCU.64) per two
+// (measured: K1 -3 %, K2 -1 %).  The biases stay in the constant bank: an LDS in the middle of the MUFU-bound sine
+// epilogues competes with the MUFU for the MIO queue and made K1 6 % slower.
+constexpr uint32_t kc1L3W = 0, kc1Floats = 1024;
+constexpr uint32_t kc2E4W = 0, kc2Floats = 768;
+constexpr uint32_t k1Part = k1WBytes, k1Const = k1Part + 2 * 128 * 16, k1Bars = k1Const + kc1Floats * 4, k1Smem = k1Bars + 128;
+// K2: E1 | E2 | E3 | A0[2 WGs] (tap staging of the NEXT tile aliases the A tile once the first MMA has read it) |
+//     partial-sum exchange | fp32 constants
 constexpr uint32_t k2E1 = 0, k2E2 = k2E1 + kW64x64, k2E3 = k2E2 + kW256x64, k2WBytes = k2E3 + kW256x256;
-constexpr uint32_t k2A0 = k2WBytes, k2Taps = k2A0 + 2 * 16384, k2Bars = k2Taps + 16 * 1536, k2Smem = k2Bars + 128;
+constexpr uint32_t k2A0 = k2WBytes, k2Part = k2A0 + 2 * 16384, k2Const = k2Part + 2 * 128 * 16, k2Bars = k2Const + kc2Floats * 4,
+                   k2Smem = k2Bars + 128;
 // K0: A tile (4 K-blocks x 128 rows) | W_tab (4 K-blocks x 256 rows)
 constexpr uint32_t k0A = 0, k0B = 4 * 128 * 128, k0WBytes = 4 * 256 * 128, k0Bars = k0B + k0WBytes, k0Smem = k0Bars + 128;
 static_assert(k2A0 % 1024 == 0 && k1F3 % 1024 == 0 && k1L1 % 1024 == 0 && k2E3 % 1024 == 0 && k0B % 1024 == 0,
@@ -529,6 +537,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
   const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
   const uint4* __restrict__ tab4 = reinterpret_cast<const uint4*>(p.tab);  // 32 uint4 per texel
   float4* part = reinterpret_cast<float4*>(smem + k1Part) + cx.wg * 128;
+  const float* cs = reinterpret_cast<const float*>(smem + k1Const);   // shared-memory copy of the fp32 output layer
   const int ch0 = CH * 32;   // this thread's 32 channels of every 64-wide vector
 
   const long tile_first = (long)blockIdx.x * 2 + cx.wg;
@@ -614,7 +623,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
-                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, p.c.l3_w + 64 * i + ch0, fl, pf); });
+                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
     // combine the two column halves and store
     if constexpr (ISSUER) continue;
     const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
@@ -630,6 +639,11 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
 
 __global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
   const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
+  {
+    float* cs = reinterpret_cast<float*>(smem + k1Const);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) cs[kc1L3W + i] = p.c.l3_w[i];
+    __syncthreads();
+  }
   WgCtx cx = make_wg(s);
   if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
@@ -662,6 +676,11 @@ __device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bo
   return (long)min(y, p.row_end - 1) * p.g.WW + min(x, p.g.WW - 1);
 }
 
+// Tap staging of a warp's 16 queries lives INSIDE the warp's own 16 rows (2 KB) of the WG's A tile: query group it
+// (4 queries, 384 B of taps) sits at the start of rows [4 it, 4 it + 4) (512 B; the SW128 swizzle stays inside a row),
+// which phase 2 overwrites only after it has read that group's taps.  uint4 index of query qi's 6-entry slot:
+__device__ __forceinline__ int tap_slot(int qi) { return (qi >> 2) * 32 + (qi & 3) * 6; }
+
 // phase 1 (bilinear footprints -> per-warp staging); issued one tile ahead, under the 256->256 layer's first MMA wait
 __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile, int warp_in_wg, int lane) {
   const Geometry& g = p.g;
@@ -686,7 +705,7 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
       if (lr.w[k] == 0.f) lr.off[k] = 0;
     }
     const uint32_t cb = which * 128u;
-    uint4* dst = stg + qi * 6;
+    uint4* dst = stg + tap_slot(qi);
     dst[which * 2 + 0] = make_uint4((uint32_t)hr.off[0] * 256u + cb, (uint32_t)hr.off[1] * 256u + cb,
                                     (uint32_t)hr.off[2] * 256u + cb, (uint32_t)hr.off[3] * 256u + cb);
     dst[which * 2 + 1] = make_uint4((uint32_t)lr.off[0] * 512u + 256u + cb, (uint32_t)lr.off[1] * 512u + 256u + cb,
@@ -712,7 +731,7 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
   uint32_t wa[4], wb[4];
   auto load_step = [&](int s_, uint4 (&v)[8], uint32_t (&w)[4]) {
     const int qloc = (s_ >> 1) * 4 + (lane >> 3), which = s_ & 1;
-    const uint4* sq = stg + qloc * 6;
+    const uint4* sq = stg + tap_slot(qloc);
     const uint4 oh = sq[which * 2 + 0], ol = sq[which * 2 + 1], wq = sq[4 + which];
     const uint32_t off[8] = {oh.x, oh.y, oh.z, oh.w, ol.x, ol.y, ol.z, ol.w};
     w[0] = wq.x; w[1] = wq.y; w[2] = wq.z; w[3] = wq.w;
@@ -766,8 +785,9 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   const uint32_t wsm = smem_u32(smem);
   const int lane = threadIdx.x & 31, warp = cx.slot & 15, warp_in_wg = cx.warp_in_wg;
   uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
-  uint4* stg = reinterpret_cast<uint4*>(smem + k2Taps + warp * 1536);
-  float4* part = reinterpret_cast<float4*>(a0);   // partial-sum exchange reuses the WG's A tile (dead after the first MMA)
+  uint4* stg = reinterpret_cast<uint4*>(a0 + warp_in_wg * 2048);
+  float4* part = reinterpret_cast<float4*>(smem + k2Part) + cx.wg * 128;
+  const float* cs = reinterpret_cast<const float*>(smem + k2Const);   // shared-memory copy of the fp32 output layer
   const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
   const int ch0 = CH * 32;
 
@@ -815,7 +835,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
       if (tile_next < ntiles && !ISSUER) k2_gather_taps(p, stg, tile_next, warp_in_wg, lane);
     }
     layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
-                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, p.c.e4_w + 64 * i + ch0, rgb, pf); });
+                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf); });
     if constexpr (ISSUER) continue;
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
@@ -826,13 +846,18 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
       p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
       p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
     }
-    // the next tile's gather rewrites the A tile `part` aliases: every reader must be done
-    wg_barrier(cx.wg);
+    // (`part` is rewritten one whole tile later; no warp can run that far ahead of a sibling: every chunk's MMA waits
+    // for all eight warps' arrival on the step barrier)
   }
 }
 
 __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
+  {
+    float* cs = reinterpret_cast<float*>(smem + k2Const);
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) cs[kc2E4W + i] = p.c.e4_w[i];
+    __syncthreads();
+  }
   WgCtx cx = make_wg(s);
   if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
