@@ -156,6 +156,13 @@ int stif_debug_last_flow(stif_decoder_t* dec, float* flow_host, size_t num_float
  * these knobs).  Values <= 0 leave a knob unchanged; *respins (may be NULL) receives how many times a repeat was needed. */
 int stif_debug_host_pipeline(stif_decoder_t* dec, int bands, int halo, int64_t* respins);
 
+/* The band plan stif_decode_host would use (pure host arithmetic, no device needed): for a [H,W] -> [HH,WW] decode of T
+ * timesteps with the given band-count hint (`bands_forced` != 0 takes it literally), halo and SM count, writes per band
+ * the LR rows that must have been uploaded, the end of stage A+B and the end of stage C-E in HR rows (arrays of
+ * `max_entries`), the cost model's estimate in microseconds (may be NULL) and returns the number of bands (< 0: error). */
+int stif_debug_band_plan(int H, int W, int HH, int WW, int T, int bands, int bands_forced, int halo, int num_sms,
+                         int max_entries, int* lr_end, int* ab_end, int* ce_end, double* cost_us);
+
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t stif_launch_count(const stif_decoder_t* dec);
 

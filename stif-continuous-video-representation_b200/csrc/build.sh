@@ -12,7 +12,7 @@ for f in stif_api.cu kernels_fp32.cu kernels_tc.cu tc_selftest.cu; do
   ( "$NVCC" $ARCH $CXXFLAGS ${EXTRA_NVCC_FLAGS:-} -c "$HERE/$f" -o "$HERE/obj/${f%.cu}.o" ) &
   pids+=($!)
 done
-for f in pack_weights.cpp axis_tables.cpp; do
+for f in pack_weights.cpp axis_tables.cpp host_plan.cpp; do
   ( "$NVCC" $ARCH $CXXFLAGS -c "$HERE/$f" -o "$HERE/obj/${f%.cpp}.o" ) &
   pids+=($!)
 done

@@ -244,7 +244,7 @@ struct HostPipe {
 };
 
 // Number of timesteps whose Q table + flow stay resident at once in the banded host pipeline.
-constexpr int kHostGroup = 4;
+constexpr int kHostGroup = kMaxHostGroup;
 size_t host_group_extra_bytes(int HH, int WW, int T) {
   const size_t Q = (size_t)HH * WW;
   return (size_t)(std::min(T, kHostGroup) - 1) * (align256(Q * 128 * 2) + align256(Q * 4 * sizeof(float)));
@@ -279,73 +279,9 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
     return w;
   };
   const int halo = std::min(HH, std::max(1, d->host_halo));
-  HostAxis ay;
-  build_axis(H, HH, ay);
-  // Band plan.  The kernels are persistent with static tile assignment, so a launch of n tiles costs ceil(n / slots)
-  // tile times (slots = 2 tiles per SM): band heights are chosen so that each launch fills just under a whole number
-  // of waves.  he[k] / ge[k] = end of band k in HR rows for stage A+B / stage C-E, lr_end[k] = LR rows the band needs.
-  const long slots = 2L * d->num_sms;
-  auto k1_tiles = [&](int rows) { return ((long)rows * WW + 127) / 128; };
-  auto k2_tiles = [&](int rows) { return (long)((rows + 7) / 8) * ((WW + 15) / 16); };
-  auto wave_aligned = [&](int target, int step, auto tiles_of) {
-    int best = std::max(step, target / step * step);
-    double best_eff = 0.0;
-    for (int r = std::max(step, (int)(0.8 * target) / step * step); r <= (int)(1.05 * target); r += step) {
-      const double w = (double)tiles_of(r) / (double)slots, eff = w / std::ceil(w);
-      if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && std::abs(r - target) < std::abs(best - target))) { best = r; best_eff = eff; }
-    }
-    return best;
-  };
-  // The first band is short (the pipeline starts after a ~0.1 ms upload; the GPU would idle otherwise), the rest are
-  // equal (heights are multiples of 8 rows so that stage C-E, whose tiles are 8 rows high, keeps pace with stage A+B),
-  // and stage C-E of the last rows is cut once more so that only a short final download is exposed.
-  auto both_tiles = [&](int rows) { return std::max(k1_tiles(rows), k2_tiles(rows)); };
-  struct Plan { std::vector<int> he, ge, lr_end; double cost_us; };
-  auto make_plan = [&](int nb) {
-    const int n_entries = nb > 1 ? nb + 1 : 1;
-    Plan pl{std::vector<int>(n_entries, HH), std::vector<int>(n_entries, HH), std::vector<int>(n_entries, H), 0.0};
-    const int first = std::max(8, (HH / (4 * std::max(nb, 1))) & ~7);
-    const int r1 = nb > 1 ? wave_aligned((HH - first) / (nb - 1), 8, both_tiles) : HH;
-    const int tail = std::min(HH / 2, wave_aligned(std::max(16, HH / 16), 8, k2_tiles));
-    for (int k = 0; k + 1 < nb; ++k) {
-      pl.he[k] = std::min(HH, first + k * r1);
-      pl.ge[k] = std::max(k ? pl.ge[k - 1] : 0, (pl.he[k] - halo) & ~7);
-      if (pl.ge[k] - (k ? pl.ge[k - 1] : 0) < 32) pl.ge[k] = k ? pl.ge[k - 1] : 0;   // too few rows for a launch: next band
-      const int last = pl.he[k] - 1;   // LR rows the footprints of HR rows < he[k] touch (tables are monotone)
-      pl.lr_end[k] = std::min(H, std::max(ay.idx[last], ay.b0[last] + 1) + 1);
-      if (k && pl.lr_end[k] < pl.lr_end[k - 1]) pl.lr_end[k] = pl.lr_end[k - 1];
-    }
-    if (nb > 1) pl.ge[nb - 1] = std::max(pl.ge[nb - 2], (HH - tail) & ~7);   // band nb-1: last upload / stage A+B; band nb: only the tail of C-E
-    nb = n_entries;
-    // cost model (microseconds; constants measured on B200, profiles/launch_overhead.py + the banded timeline): the
-    // compute stream starts band k when its upload has landed and band k-1 is done; a launch costs ~12.5 us per wave of
-    // 2 tiles/SM + 11 us fixed; PCIe moves ~55 GB/s each way; the last band's download is exposed
-    double t = 0.0;
-    for (int k = 0; k < nb; ++k) {
-      const int h0 = k ? pl.he[k - 1] : 0, g0 = k ? pl.ge[k - 1] : 0, l0 = k ? pl.lr_end[k - 1] : 0;
-      t = std::max(t, (double)pl.lr_end[k] * W * 198 * 4 / 55e3);
-      if (pl.lr_end[k] > l0) t += 11.0 + 0.3 * (pl.lr_end[k] - l0) * W / 1000.0;   // K0: fixed + ~0.3 ns per texel
-      if (pl.he[k] > h0) t += G * (12.5 * std::ceil((double)k1_tiles(pl.he[k] - h0) / slots) + 11.0);
-      if (pl.ge[k] > g0) t += G * (12.5 * std::ceil((double)k2_tiles(pl.ge[k] - g0) / slots) + 11.0);
-    }
-    t += (double)(HH - (nb > 1 ? pl.ge[nb - 2] : 0)) * WW * 12 * G / 55e3;
-    pl.cost_us = t;
-    return pl;
-  };
-  int nbands = std::max(1, std::min(hp.bands, H));
-  if (!d->host_bands_forced) {   // hp.bands is a hint: take the cheapest plan nearby (1 band for rasters too small to split)
-    int best = 1;
-    double best_cost = make_plan(1).cost_us;
-    for (int nb = std::max(2, nbands - 2); nb <= std::min(H, nbands + 4); ++nb) {
-      if (k1_tiles(HH) < 2 * slots * nb) break;   // a band would not even fill two waves
-      const double c = make_plan(nb).cost_us;
-      if (c < best_cost) { best = nb; best_cost = c; }
-    }
-    nbands = best;
-  }
-  const Plan plan = make_plan(nbands);
+  const HostBandPlan plan = plan_host_bands(H, W, HH, WW, G, hp.bands, d->host_bands_forced, halo, d->num_sms);
   const std::vector<int>&he = plan.he, &ge = plan.ge, &lr_end = plan.lr_end;
-  nbands = (int)he.size();
+  const int nbands = (int)he.size();
   std::vector<cudaEvent_t> used_events;
   auto chain = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {   // `to` waits for what `from` holds now
     cudaEvent_t ev = take_event(d);
@@ -727,6 +663,18 @@ int stif_debug_host_pipeline(stif_decoder_t* d, int bands, int halo, int64_t* re
   if (halo > 0) d->host_halo = halo;
   if (respins) *respins = d->host_respins;
   return STIF_OK;
+}
+
+int stif_debug_band_plan(int H, int W, int HH, int WW, int T, int bands, int bands_forced, int halo, int num_sms, int max_entries,
+                         int* lr_end, int* ab_end, int* ce_end, double* cost_us) {
+  if (H < 1 || W < 1 || HH < 1 || WW < 1 || T < 1 || bands < 1 || halo < 1 || num_sms < 1 || max_entries < 1 || !lr_end || !ab_end || !ce_end)
+    return set_error(STIF_EINVAL, "invalid argument");
+  const HostBandPlan pl = plan_host_bands(H, W, HH, WW, std::min(T, kMaxHostGroup), bands, bands_forced != 0, std::min(HH, halo), num_sms);
+  const int n = (int)pl.he.size();
+  if (n > max_entries) return set_error(STIF_ENOMEM, "plan has %d entries, room for %d", n, max_entries);
+  for (int k = 0; k < n; ++k) { lr_end[k] = pl.lr_end[k]; ab_end[k] = pl.he[k]; ce_end[k] = pl.ge[k]; }
+  if (cost_us) *cost_us = pl.cost_us;
+  return n;
 }
 
 int stif_axis_tables(int n_lr, int n_hr, float* coord, int32_t* index, float* rel, float* base) {

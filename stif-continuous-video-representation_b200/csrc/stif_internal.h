@@ -97,6 +97,14 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
 struct TcWeights;  // opaque: device smem images + host constant blocks
 TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err);
 void tc_weights_destroy(TcWeights*);
+// Band plan of the band-major host pipeline (host_plan.cpp).
+constexpr int kMaxHostGroup = 4;   // timesteps whose Q table + flow stay resident at once
+struct HostBandPlan {
+  std::vector<int> he, ge, lr_end;   // per band: end (HR rows) of stage A+B, of stage C-E; LR rows that must have landed
+  double cost_us;                    // the cost model's estimate of the call
+};
+HostBandPlan plan_host_bands(int H, int W, int HH, int WW, int G, int bands_hint, bool bands_forced, int halo, int num_sms);
+
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage);
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,

@@ -23,7 +23,7 @@ STIF_ABI_VERSION = 1
 EXPORTS = [
     "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
     "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_axis_tables",
-    "stif_ensemble_weights", "stif_debug_last_flow", "stif_debug_host_pipeline", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
+    "stif_ensemble_weights", "stif_debug_last_flow", "stif_debug_host_pipeline", "stif_debug_band_plan", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
 ]
 
 
@@ -54,6 +54,7 @@ def _load():
     lib.stif_ensemble_weights.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t]
     lib.stif_debug_last_flow.argtypes = [vp, fp, C.c_size_t]
     lib.stif_debug_host_pipeline.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    lib.stif_debug_band_plan.argtypes = [C.c_int] * 10 + [ip, ip, ip, C.POINTER(C.c_double)]
     lib.stif_launch_count.argtypes = [vp]
     lib.stif_launch_count.restype = C.c_int64
     lib.stif_profile_enable.argtypes = [vp, C.c_int]
@@ -101,3 +102,18 @@ def selftest(device: int = 0) -> tuple[int, str]:
     buf = C.create_string_buffer(8192)
     rc = lib.stif_selftest(device, buf, len(buf))
     return rc, buf.value.decode(errors="replace")
+
+
+def band_plan(H: int, W: int, HH: int, WW: int, T: int = 2, bands: int = 6, forced: bool = False, halo: int = 32,
+              num_sms: int = 148):
+    """Band plan of the host pipeline (``stif_debug_band_plan``): ``(lr_end, ab_end, ce_end, cost_us)`` per band."""
+    import numpy as np
+    n_max = 64
+    a, b, c = (np.zeros(n_max, np.int32) for _ in range(3))
+    cost = C.c_double(0.0)
+    ip = C.POINTER(C.c_int32)
+    n = lib.stif_debug_band_plan(H, W, HH, WW, T, bands, int(forced), halo, num_sms, n_max, a.ctypes.data_as(ip),
+                                 b.ctypes.data_as(ip), c.ctypes.data_as(ip), C.byref(cost))
+    if n < 0:
+        check(n)
+    return a[:n].copy(), b[:n].copy(), c[:n].copy(), float(cost.value)

@@ -86,3 +86,35 @@ def test_no_cpu_fallback(stif):
 def test_weight_key_order_matches_fixture_generator(stif):
     from oracle import synth
     assert stif.weight_keys() == synth.weight_keys()
+
+
+@pytest.mark.parametrize("shape", [(270, 480, 1080, 1920), (540, 960, 2160, 3840), (270, 480, 1755, 3120), (64, 64, 416, 416),
+                                   (96, 40, 384, 163), (20, 24, 13, 17), (7, 9, 1000, 33)])
+@pytest.mark.parametrize("bands,forced", [(6, False), (6, True), (3, True), (11, True)])
+@pytest.mark.parametrize("halo", [1, 32, 500])
+def test_host_band_plan_invariants(stif, shape, bands, forced, halo):
+    """The band plan of stif_decode_host's pipeline (pure host arithmetic, csrc/host_plan.cpp).  Whatever the knobs:
+    the three boundaries are monotone and complete; stage C-E never runs ahead of stage A+B, and trails it by the halo
+    wherever stage A+B is not complete yet (the speculation the kernels then verify); every HR row handed to stage A+B
+    has its nearest AND bilinear LR footprint inside the rows uploaded so far (exact, from the library's own tables)."""
+    from stif_b200 import _lib
+    H, W, HH, WW = shape
+    lr_end, ab_end, ce_end, cost = _lib.band_plan(H, W, HH, WW, T=2, bands=bands, forced=forced, halo=halo)
+    n = len(lr_end)
+    assert n >= 1 and lr_end[-1] == H and ab_end[-1] == HH and ce_end[-1] == HH and cost > 0
+    for a in (lr_end, ab_end, ce_end):
+        assert (np.diff(a) >= 0).all() and a[0] >= 0
+    assert (ce_end <= ab_end).all()
+    h = min(halo, HH)
+    for k in range(n):
+        if ab_end[k] < HH:
+            assert ce_end[k] <= max(0, ab_end[k] - h)
+    idx = stif.axis_tables(H, HH)["index"]
+    u = ((np.arange(HH, dtype=np.float64) + 0.5) / HH) * H - 0.5          # bilinear source row of each HR row centre
+    b1 = np.clip(np.floor(u).astype(np.int64) + 1, 0, H - 1)               # lower tap of the bilinear footprint
+    for k in range(n):
+        rows = ab_end[k]
+        if rows > 0:
+            assert idx[:rows].max() < lr_end[k] and b1[:rows].max() < lr_end[k], (k, rows, lr_end[k])
+    if not forced and HH * WW < 128 * 296 * 4:
+        assert n == 1                                                       # small rasters are not split
