@@ -30,6 +30,8 @@ def main() -> int:
     jobs = [(2, 64, 64, (256, 256), [i / 8 for i in range(8)], False),
             (1, 270, 480, (1080, 1920), [0.5], False),
             (1, 48, 40, (163, 141), [0.25], True)]
+    if world >= 8:   # BASELINE.json config 4: 4K output, x8 temporal, one timestep per GPU
+        jobs.append((1, 540, 960, (2160, 3840), [i / 8 for i in range(8)], False))
     for P, H, W, out_size, times, stress in jobs:
         launcher = QueryShardLauncher(mode="bf16")
         weights = synth.make_weights(3, stress) if rank == 0 else None
@@ -42,6 +44,11 @@ def main() -> int:
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
+        results = launcher.decode(times, out_size, halo=8)
+        torch.cuda.synchronize()
+        dt_local = time.perf_counter() - t0
+        dist.barrier()
+        t0 = time.perf_counter()                      # second pass: workspaces exist, geometry tables cached
         results = launcher.decode(times, out_size, halo=8)
         torch.cuda.synchronize()
         dt_local = time.perf_counter() - t0
@@ -58,7 +65,7 @@ def main() -> int:
             kind = "slabs" if all(u.row_begin == 0 and u.row_end == out_size[0] for u in units) else "row bands"
             q = P * len(times) * out_size[0] * out_size[1]
             print(f"job {P}x{H}x{W} -> {out_size} T={len(times)} on {world} GPUs: {len(units)} units ({kind}), "
-                  f"decode {float(t.item()) * 1e3:.2f} ms ({q / float(t.item()):.3e} q/s incl. first-call setup), "
+                  f"decode {float(t.item()) * 1e3:.2f} ms ({q / float(t.item()):.3e} q/s, second pass), "
                   f"gathered == single-GPU decode: {same}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
