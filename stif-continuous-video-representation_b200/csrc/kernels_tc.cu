@@ -162,25 +162,32 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
   ++cx.n_steps;
 }
 
-// K2: the two workgroups take turns at the gather (named barrier 7: 256 arriving + 256 waiting threads).  Left alone they
-// drift into lockstep -- the trailing WG finds its neighbour tile's table lines in L1 and catches up -- and then both sit
-// in their gather (memory latency, MUFU idle) and both fight for the MUFU in their sine epilogues at the same time.
-// WG1 may start the gather of its j-th tile only after WG0 has finished the gather of ITS j-th tile; WG0 never waits (a
-// handshake in both directions at the half-tile points serialised the WGs and was 25 % slower).  Measured: K2 -6 %.
+// K2: the two workgroups take turns at the gather.  Left alone they drift into lockstep -- the trailing WG finds its
+// neighbour tile's table lines in L1 and catches up -- and then both sit in their gather (memory latency, MUFU idle)
+// and both run their sine epilogues at the same time.  WG1 may start the gather of its j-th tile only after WG0 has
+// finished the gather of ITS j-th tile (named barrier 7: WG0's 256 threads arrive, WG1's 256 sync).  Measured: K2 -6 %.
+// WG0 in turn may not signal tile j+1 before WG1 has taken the signal for tile j (barrier 8, roles swapped).  That second
+// barrier costs WG0 nothing in steady state (WG1 picked the previous signal up a whole tile ago) but it is REQUIRED:
+// without it WG0 can get two tiles ahead, and two arrivals of the same 256 threads complete a 512-thread phase of
+// barrier 7 on their own -- the pairing is lost and WG1's last sync waits forever (seen as a hang at 4K).  (A handshake
+// in both directions at the half-tile points, by contrast, serialised the WGs and was 25 % slower.)
 #ifndef STIF_GATHER_TURNS
 #define STIF_GATHER_TURNS 1
 #endif
-__device__ __forceinline__ int wg1_tile_count(long ntiles) {   // tiles WG1 of this CTA will process (<= WG0's count)
-  const long stride = 2L * gridDim.x, first = 2L * blockIdx.x + 1;
-  return first < ntiles ? (int)((ntiles - first + stride - 1) / stride) : 0;
-}
+// Both sides are unconditional (no tile counts): WG0 has as many tiles as WG1 or one more, so every sync finds its
+// partner; the at most one unmatched arrival per barrier is the very last one and nobody waits behind it.
+// WG1, top of every tile: wait for WG0's signal, acknowledge it.
 __device__ __forceinline__ void gather_turn_wait(const WgCtx& cx) {
-  if (STIF_GATHER_TURNS && cx.wg == 1) asm volatile("bar.sync 7, 512;" ::: "memory");
+  if (STIF_GATHER_TURNS && cx.wg == 1) {
+    asm volatile("bar.sync 7, 512;" ::: "memory");
+    asm volatile("bar.arrive 8, 512;" ::: "memory");
+  }
 }
-__device__ __forceinline__ void gather_turn_done(const WgCtx& cx, int& turns_left) {
-  if (STIF_GATHER_TURNS && cx.wg == 0 && turns_left > 0) {
+// WG0, after the gather of every tile: take WG1's acknowledgement of the previous signal (none before the first), signal.
+__device__ __forceinline__ void gather_turn_done(const WgCtx& cx, bool first_tile) {
+  if (STIF_GATHER_TURNS && cx.wg == 0) {
+    if (!first_tile) asm volatile("bar.sync 8, 512;" ::: "memory");
     asm volatile("bar.arrive 7, 512;" ::: "memory");
-    --turns_left;
   }
 }
 
@@ -809,7 +816,6 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
   const int ch0 = CH * 32;
 
-  int turns_left = wg1_tile_count(ntiles);
   const long tile_first = (long)blockIdx.x * 2 + cx.wg;
   if (tile_first < ntiles && !ISSUER) k2_gather_taps(p, stg, tile_first, warp_in_wg, lane);
   for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
@@ -842,7 +848,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     step_done<ISSUER>(cx);
     trace_mark(cx, 3);
 
-    if constexpr (!ISSUER) gather_turn_done(cx, turns_left);
+    if constexpr (!ISSUER) gather_turn_done(cx, tile == tile_first);
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
     run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
