@@ -15,6 +15,18 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    config.addinivalue_line("markers", "timeout: per-test limit (pytest-timeout; ignored if the plugin is absent)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Every GPU test gets a 150 s limit (pytest-timeout, thread method: the process is torn down, which also tears down a
+    hung CUDA context).  The persistent kernels synchronise with named barriers that have no timeout of their own; a
+    protocol bug must fail one test fast, not stall the whole run."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(150, method="thread"))
 
 
 @pytest.fixture(scope="session")
