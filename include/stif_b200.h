@@ -50,7 +50,7 @@ extern "C" {
 #define STIF_MODE_BF16      0  /* tcgen05 bf16 tensor-core kernels, fp32 accumulate; RGB within 2e-2 of the reference */
 #define STIF_MODE_FP32      1  /* fp32 FMA-pipe kernels; RGB within 1e-4 of the reference                           */
 /* flags OR-ed into `mode` */
-#define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085) */
+#define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085), either precision mode */
 #define STIF_FLAG_OUT_U8         0x200  /* write what the reference's caller makes of the result (custom_video_test.py:102):
                                          * `(img.clamp(0,1).permute(1,2,0) * 255).astype(uint8)` -- uint8 [T,B,HH,WW,3],
                                          * fp32 clamp / multiply, truncation.  The `out` pointer is then a uint8_t buffer and
@@ -97,7 +97,7 @@ size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode
  *               (Sakuya_arch_test.py:368-371); the x4 default is (4H,4W)
  *   out_rgb_dev [T,B,3,HH,WW] fp32, unclamped (== torch.stack(preds));
  *               with STIF_FLAG_OUT_U8: uint8 [T,B,HH,WW,3] (see the flag)
- * With STIF_FLAG_LOCAL_ENSEMBLE (STIF_MODE_FP32 only in this build) the result is
+ * With STIF_FLAG_LOCAL_ENSEMBLE the result is
  * decoding_localensemble's: B must be 1 as in the reference, out is [T,1,3,HH,WW]. */
 int stif_decode(stif_decoder_t* dec,
                 const float* latent_dev, const float* frames_dev,

@@ -304,6 +304,14 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
   return cudaSuccess;
 }
 
+cudaError_t ensemble_blend_launch(const LaunchCtx& cx, const float* pred, float* out_rgb, int HH, int WW, const AxisTables ens_y[2],
+                                  const AxisTables ens_x[2], int k) {
+  const long Q = (long)HH * WW;
+  ensemble_blend<<<(unsigned)((Q + 255) / 256), 256, 0, cx.stream>>>(pred, out_rgb, WW, Q, ens_y[0], ens_y[1], ens_x[0], ens_x[1], k);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
 cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw,
                                       const Geometry geo_pass[4], const AxisTables ens_y[2], const AxisTables ens_x[2],
                                       const Workspace& ws, float t, float* out_rgb) {

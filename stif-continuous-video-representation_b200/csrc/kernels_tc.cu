@@ -89,6 +89,7 @@ struct K1Params {
   const __half* tab;   // [H*W,256]   TA | TB | TE1 | TE2
   __half* qtab;        // [HH*WW,128] Q1 | Q2
   float* flow;         // [HH*WW,4]
+  float* ftab;         // local-ensemble passes only: F + composed bias, [HH*WW,64] fp32 (stage B reads it at OTHER pixels)
   const uint8_t* wimg;
   long q_begin, q_end;
   long long* trace;    // debug: clock64 timestamps of block 0 (STIF_TRACE=<file>), else null
@@ -370,6 +371,24 @@ __device__ __forceinline__ void epi_store_qtab(uint32_t (&v)[32], const float* _
   if (!valid) return;
   stg256(dst, o);            // two full 32-byte sectors per thread
   stg256(dst + 16, o + 8);
+}
+
+// local-ensemble stage A: F + bias -> fp32 table row (this thread's 32 channels = one 128-byte line)
+template <class Pf>
+__device__ __forceinline__ void epi_store_ftab(uint32_t (&v)[32], const float* __restrict__ bias, float* dst, bool valid, Pf&& next_ld) {
+  uint32_t o[32];
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    const float4 b4 = ldc4(bias + 4 * j4);
+    const float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
+    const float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
+    o[4 * j4] = __float_as_uint(a0.x); o[4 * j4 + 1] = __float_as_uint(a0.y);
+    o[4 * j4 + 2] = __float_as_uint(a1.x); o[4 * j4 + 3] = __float_as_uint(a1.y);
+  }
+  next_ld();
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) stg256(dst + 8 * j, o + 8 * j);
 }
 
 // f0 = sin(F + g) -> bf16 -> TMEM (g already holds bilinear(TB) + time constant + composed bias)
@@ -681,6 +700,133 @@ __global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_consta
   cta_epilogue(s.tmem_base, 512);
 }
 
+// ---- decoding_localensemble passes (Sakuya_arch_test.py:962-1085) ------------------------------------------------
+// Every gather of a pass uses coordinates shifted by half an LR texel (the per-pass axis tables in p.g), including the
+// "identity" nearest gather of HRfeat in stage B: F is needed at ANOTHER pixel (g.y.hidx / g.x.hidx), so stage A and
+// stage B cannot share a tile.  PASS 1 = stage A for the raster: Q1 | Q2 (fp16) and F + bias (fp32) tables.
+// PASS 2 = stage B: f0 = sin(F[hidx] + bilinear(TB) + cB) -> flow_imnet -> flow.  Same building blocks as the fused loop.
+template <bool ISSUER, int PASS>
+__device__ __forceinline__ void k1_ens_tile_loop(const K1Params& p, const CtaSetup& s, WgCtx& cx) {
+  const int CH = cx.colhalf;
+  const uint32_t wsm = smem_u32(smem);
+  const Geometry& g = p.g;
+  const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
+  const uint4* __restrict__ tab4 = reinterpret_cast<const uint4*>(p.tab);
+  float4* part = reinterpret_cast<float4*>(smem + k1Part) + cx.wg * 128;
+  const float* cs = reinterpret_cast<const float*>(smem + k1Const);
+  const int ch0 = CH * 32;
+  for (long tile = (long)blockIdx.x * 2 + cx.wg; tile < ntiles; tile += (long)gridDim.x * 2) {
+    const long q = p.q_begin + tile * kTile + cx.row;
+    const bool valid = q < p.q_end;
+    const long qc = valid ? q : p.q_end - 1;
+    const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
+    if constexpr (PASS == 1) {
+      if constexpr (!ISSUER) {   // stage A first layer, exactly as in the fused loop
+        const int iy = g.y.idx[jy], ix = g.x.idx[jx];
+        const float rely = g.y.rel[jy], relx = g.x.rel[jx];
+        const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
+        const uint4* ta = tab4 + (inb ? ((long)iy * g.W + ix) : 0) * 32 + CH * 4;
+        uint32_t pk[16];
+        U8x32 ta2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((j & 1) == 0) ta2 = ldg256(ta + j);
+          uint32_t w4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w4[e] = inb ? ta2.r[(j & 1) * 4 + e] : 0u;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = ch0 + j * 8 + e * 2;
+            const float b0 = fmaf(rely, p.c.a_rel[2 * c], fmaf(relx, p.c.a_rel[2 * c + 1], p.c.cA[c]));
+            const float b1 = fmaf(rely, p.c.a_rel[2 * c + 2], fmaf(relx, p.c.a_rel[2 * c + 3], p.c.cA[c + 1]));
+            pk[j * 4 + e] = pack_bf16x2(fast_sin(add_f16((uint16_t)(w4[e] & 0xFFFF), b0)), fast_sin(add_f16((uint16_t)(w4[e] >> 16), b1)));
+          }
+        }
+        tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      step_done<ISSUER>(cx);
+      run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F1, 64, [](int) { return 0; },
+                   [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
+      run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+        epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
+      });
+      auto f3_order = [](int i) { return i == 2 ? 0 : i + 1; };
+      run_layer<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
+        if (i < 2) epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
+        else epi_store_ftab(v, p.c.f3_b + ch0, p.ftab + qc * 64 + ch0, valid, pf);
+      });
+    } else {
+      if constexpr (!ISSUER) {   // f0 = sin(F[shifted nearest HR pixel] + bilinear(TB; shifted position) + cB)    (:1003-1030)
+        float gB[32];
+        const Taps tp = make_taps_tables(g, jy, jx);
+        uint16_t wq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wq[k] = __half_as_ushort(__float2half_rn(tp.w[k]));
+        const int hy = g.y.hidx[jy], hx = g.x.hidx[jx];
+        const bool hin = (hy >= 0) & (hy < g.HH) & (hx >= 0) & (hx < g.WW);   // zero padding of the nearest gather
+        const float* frow = p.ftab + ((long)(hin ? hy : 0) * g.WW + (hin ? hx : 0)) * 64 + ch0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const U8x32 f0 = ldg256(frow + 16 * j), f1 = ldg256(frow + 16 * j + 8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            gB[16 * j + e] = p.c.cB[ch0 + 16 * j + e] + (hin ? __uint_as_float(f0.r[e]) : 0.f);
+            gB[16 * j + 8 + e] = p.c.cB[ch0 + 16 * j + 8 + e] + (hin ? __uint_as_float(f1.r[e]) : 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const U8x32 v = ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              gB[16 * j + 2 * e] = fma_f16((uint16_t)(v.r[e] & 0xFFFF), wq[k], gB[16 * j + 2 * e]);
+              gB[16 * j + 2 * e + 1] = fma_f16((uint16_t)(v.r[e] >> 16), wq[k], gB[16 * j + 2 * e + 1]);
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(fast_sin(gB[2 * j]), fast_sin(gB[2 * j + 1]));
+        tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      step_done<ISSUER>(cx);
+      run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
+                   [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
+      float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+      run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
+                   [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
+      if constexpr (ISSUER) continue;
+      const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
+      if (CH == 1) part[cx.row] = mine;
+      wg_barrier(cx.wg);
+      if (CH == 0 && valid) {
+        const float4 o = part[cx.row];
+        reinterpret_cast<float4*>(p.flow)[q] =
+            make_float4(mine.x + o.x + p.c.l3_b[0], mine.y + o.y + p.c.l3_b[1], mine.z + o.z + p.c.l3_b[2], mine.w + o.w + p.c.l3_b[3]);
+      }
+      wg_barrier(cx.wg);   // `part` is rewritten one short tile later
+    }
+  }
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(576, 1) k1_ensemble_kernel(const __grid_constant__ K1Params p) {
+  const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
+  {
+    float* cs = reinterpret_cast<float*>(smem + k1Const);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) cs[kc1L3W + i] = p.c.l3_w[i];
+    __syncthreads();
+  }
+  WgCtx cx = make_wg(s);
+  mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.issuer) k1_ens_tile_loop<true, PASS>(p, s, cx);
+  else k1_ens_tile_loop<false, PASS>(p, s, cx);
+  cta_epilogue(s.tmem_base, 512);
+}
+
 // =================================================================================================
 // K2: stage C + D + E
 // =================================================================================================
@@ -955,6 +1101,8 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k0_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (getenv("STIF_DEBUG_ATTRS")) {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k1_stage_ab_kernel);
@@ -1051,7 +1199,7 @@ void trace_dump(const char* kernel, cudaStream_t stream) {
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage) {
   const long WW = geo.WW;
-  if (stage == 1) {
+  if (stage == 1 || stage == 3 || stage == 4) {   // 1: fused stage A+B; 3 / 4: stage A / stage B of a local-ensemble pass
     K1Params p;
     p.c = tw->c1;
     for (int c = 0; c < 64; ++c) {
@@ -1062,6 +1210,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.tab = reinterpret_cast<const __half*>(ws.tab);
     p.qtab = reinterpret_cast<__half*>(ws.qtab);
     p.flow = ws.flow;
+    p.ftab = ws.ftab;
     p.wimg = tw->d_k1;
     p.q_begin = k1_row_begin * WW;
     p.q_end = k1_row_end * WW;
@@ -1070,7 +1219,11 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.trace = trace_buffer();
     p.dephase_clk = dephase_clocks(1);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
-    if (cudaError_t e = launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)) return e;
+    if (stage != 1 && !ws.ftab) return cudaErrorInvalidValue;
+    if (cudaError_t e = stage == 1   ? launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)
+                        : stage == 3 ? launch_pdl(k1_ensemble_kernel<1>, grid, 576, k1Smem, cx.stream, p)
+                                     : launch_pdl(k1_ensemble_kernel<2>, grid, 576, k1Smem, cx.stream, p))
+      return e;
     ++*cx.launch_counter;
     trace_dump("K1", cx.stream);
     return cudaGetLastError();
@@ -1100,6 +1253,21 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
   return cudaGetLastError();
+}
+
+// decoding_localensemble on the tensor-core kernels: four passes (shifted axis tables), each = stage A for the raster
+// (Q + F tables), stage B (F gathered at the shifted nearest HR pixel), stage C-E into the pass prediction, then the
+// area-weighted accumulation (bit-exact weights, kernels_fp32.cu).
+cudaError_t decode_slab_tc_ensemble(const LaunchCtx& cx, const TcWeights* tw, const Geometry geo_pass[4], const AxisTables ens_y[2],
+                                    const AxisTables ens_x[2], const Workspace& ws, float t, float* out_rgb) {
+  for (int k = 0; k < 4; ++k) {
+    const Geometry& geo = geo_pass[k];
+    for (int stage : {3, 4})
+      if (cudaError_t e = decode_slab_tc(cx, tw, geo, ws, t, 0, geo.HH, 0, geo.HH, ws.pred, stage)) return e;
+    if (cudaError_t e = decode_slab_tc(cx, tw, geo, ws, t, 0, geo.HH, 0, geo.HH, ws.pred, 2)) return e;
+    if (cudaError_t e = ensemble_blend_launch(cx, ws.pred, out_rgb, geo.HH, geo.WW, ens_y, ens_x, k)) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace stif

@@ -127,6 +127,10 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
     }
   } else {
     ws.chunk = Q;
+    if (mode & STIF_FLAG_LOCAL_ENSEMBLE) {
+      ws.ftab = (float*)take(Q * 64 * sizeof(float));
+      ws.pred = (float*)take(Q * 3 * sizeof(float));
+    }
   }
   ws.total_bytes = off;
   return ws;
@@ -431,8 +435,6 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   const int prec = mode & 0xFF;
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
   const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0, u8 = (mode & STIF_FLAG_OUT_U8) != 0;
-  if (ensemble && prec != STIF_MODE_FP32)
-    return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE is only available with STIF_MODE_FP32 in this build");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
   if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
@@ -480,7 +482,9 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
         DeviceGeometry* dg = nullptr;
         if (int rc = get_ensemble_geometry(d, H, W, HH, WW, &dg)) return rc;
         ScopedSpan sp(d, stream, 1);
-        cudaError_t e = decode_slab_fp32_ensemble(cx, d->w32, d->hw, dg->geo_pass, dg->ens_y, dg->ens_x, ws, t, out_slab);
+        cudaError_t e = prec == STIF_MODE_FP32
+                            ? decode_slab_fp32_ensemble(cx, d->w32, d->hw, dg->geo_pass, dg->ens_y, dg->ens_x, ws, t, out_slab)
+                            : decode_slab_tc_ensemble(cx, d->tcw, dg->geo_pass, dg->ens_y, dg->ens_x, ws, t, out_slab);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
       for (int stage = 1; stage <= 2 && !ensemble; ++stage) {

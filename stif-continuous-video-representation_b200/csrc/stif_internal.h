@@ -87,6 +87,12 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
                              int k1_row_end, float* out_rgb /* [3,HH,WW] */, int stage /* 1 = K1 (A+B), 2 = K2 (C+D+E) */);
 // decoding_localensemble (Sakuya_arch_test.py:962-1085): 4 shifted passes blended by swapped areas.  geo_pass[k] carries the
 // shifted axis tables of pass k (loop order (vx,vy) = (-1,-1),(-1,1),(1,-1),(1,1)); ens_y/ens_x = tables for sign -1, +1.
+struct TcWeights;
+// pass k of decoding_localensemble: out (+)= pred * area_{3-k} / tot_area (bit-exact weights)
+cudaError_t ensemble_blend_launch(const LaunchCtx& cx, const float* pred, float* out_rgb, int HH, int WW, const AxisTables ens_y[2],
+                                  const AxisTables ens_x[2], int k);
+cudaError_t decode_slab_tc_ensemble(const LaunchCtx& cx, const TcWeights* tw, const Geometry geo_pass[4], const AxisTables ens_y[2],
+                                    const AxisTables ens_x[2], const Workspace& ws, float t, float* out_rgb);
 // custom_video_test.py:102 output conversion: planar fp32 [3,HH*WW] -> uint8 HWC, rows [row_begin,row_end)
 cudaError_t rgb_to_u8_hwc(const LaunchCtx& cx, const float* rgb_planar, uint8_t* out_hwc, int HH, int WW, int row_begin, int row_end);
 cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw,

@@ -180,12 +180,13 @@ class STIFQueryDecoder(torch.nn.Module):
         """``LunaTokis.decoding`` return convention: list of ``T`` tensors ``[B,3,HH,WW]``."""
         return list(self.decode_stacked(latent, frames, times, scale, mode).unbind(0))
 
-    def decode_localensemble(self, latent, frames, times, scale=None) -> torch.Tensor:
+    def decode_localensemble(self, latent, frames, times, scale=None, mode: str | None = None) -> torch.Tensor:
         """``LunaTokis.decoding_localensemble`` (``Sakuya_arch_test.py:962-1085``): four shifted passes blended by
-        swapped areas; batch size 1, returns ``[T,3,HH,WW]``.  fp32 kernels only in this build."""
+        swapped areas (blend weights bit-exact in both modes); batch size 1, returns ``[T,3,HH,WW]``.  ``mode`` defaults
+        to the decoder's: "bf16" = tensor-core kernels (RGB within 2e-2), "fp32" = fp32 kernels (within 1e-4)."""
         if latent.shape[0] != 1:
             raise ValueError("decoding_localensemble requires batch size 1 (Sakuya_arch_test.py:989)")
-        return self.decode_stacked(latent, frames, list(times), scale, mode="fp32", local_ensemble=True)[:, 0]
+        return self.decode_stacked(latent, frames, list(times), scale, mode=mode or self.mode, local_ensemble=True)[:, 0]
 
     def decode_host(self, latent: np.ndarray | torch.Tensor, frames, times, scale=None, mode: str | None = None,
                     out: torch.Tensor | None = None, uint8: bool = False) -> torch.Tensor:
