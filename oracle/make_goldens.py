@@ -122,6 +122,38 @@ def run_case(name: str, cfg: dict) -> dict:
     return out
 
 
+TEST_VARIANT_CASES = {
+    # decoding_test (Sakuya_arch_test.py:461-598): frames x4-upsampled before the bilinear taps; int scale only
+    "testvar_x4_init": dict(H=16, W=16, scale=None, times=[0.0, 0.375], wseed=0, stress=False, iseed=0, latent_std=0.05),
+    "testvar_x3_stress": dict(H=12, W=10, scale=3, times=[0.25, 0.8], wseed=2, stress=True, iseed=7, latent_std=0.3),
+    "testvar_x5_stress": dict(H=9, W=14, scale=5, times=[0.6], wseed=3, stress=True, iseed=8, latent_std=1.0),
+}
+
+
+def run_test_variant(cfg: dict) -> dict:
+    """`LunaTokis.decoding_test(times, scale)` on seeded inputs: full RGB + the flow of every timestep."""
+    import torch
+
+    weights = synth.make_weights(cfg["wseed"], cfg["stress"])
+    latent, frames = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    model = build_reference_model(weights)
+    clear_warp_cache()
+    model.feat = torch.from_numpy(latent)
+    model.inp = torch.from_numpy(frames)
+    times = [torch.tensor([[float(t)]], dtype=torch.float32) for t in cfg["times"]]
+    flows = []
+    hook = model.flow_imnet.register_forward_hook(lambda mod, inp, out: flows.append(out.detach().numpy().copy()))
+    with torch.no_grad():
+        preds = model.decoding_test(times, cfg["scale"])
+    hook.remove()
+    Q = preds[0].shape[-2] * preds[0].shape[-1]
+    # the method runs flow_imnet on three query chunks per timestep (:519-527): stitch them back
+    per_t = [np.concatenate(flows[3 * c:3 * c + 3], 0) for c in range(len(times))]
+    assert all(f.shape == (Q, 4) for f in per_t)
+    return {"rgb": np.stack([p.numpy() for p in preds], 0).astype(np.float32), "flow": np.stack(per_t, 0).astype(np.float32),
+            "input_checksum": np.float64(checksum(latent, frames)), "weight_checksum": np.float64(checksum(*weights.values()))}
+
+
 def run_config1(stress: bool) -> dict:
     """Config 1 of BASELINE.json (64x64 latent -> 256x256, 8 timesteps): store a strided sample."""
     import torch
@@ -205,6 +237,10 @@ def main():
         res = run_config1(stress)
         np.savez_compressed(os.path.join(GOLD, f"config1_{'stress' if stress else 'init'}.npz"), **res)
         print("config1", stress, res["absmax"])
+    for name, cfg in TEST_VARIANT_CASES.items():
+        res = run_test_variant(cfg)
+        np.savez_compressed(os.path.join(GOLD, f"case_{name}.npz"), **res)
+        print(name, res["rgb"].shape)
     np.savez_compressed(os.path.join(GOLD, "e2e_small.npz"), **run_e2e_small())
     np.savez_compressed(os.path.join(GOLD, "axis_tables.npz"), **axis_goldens())
     print("done")

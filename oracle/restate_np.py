@@ -139,9 +139,35 @@ def _times_matrix(times, B: int) -> np.ndarray:
     return t
 
 
+def upsample4_bilinear(img: np.ndarray) -> np.ndarray:
+    """``F.upsample(x, scale_factor=4, mode='bilinear')`` (``Sakuya_arch_test.py:514``; align_corners=False) for ``[C,H,W]``:
+    ATen ``area_pixel_compute_source_index``: ``src = max(0, 0.25*(dst+0.5) - 0.5)`` in fp32, taps ``i0 = floor(src)``,
+    ``i1 = min(i0+1, n-1)``, weights ``(1-l, l)`` with ``l = src - i0``; rows first, then columns, fp32 throughout."""
+    img = np.asarray(img, dtype=F32)
+    C, H, W = img.shape
+
+    def axis(n):
+        dst = np.arange(4 * n, dtype=F32)
+        src = np.maximum(F32(0.0), (F32(0.25) * (dst + F32(0.5)) - F32(0.5)).astype(F32)).astype(F32)
+        i0 = np.floor(src).astype(np.int64)
+        i1 = np.minimum(i0 + 1, n - 1)
+        l1 = (src - i0.astype(F32)).astype(F32)
+        return i0, i1, (F32(1.0) - l1).astype(F32), l1
+
+    y0, y1, wy0, wy1 = axis(H)
+    x0, x1, wx0, wx1 = axis(W)
+    # ATen's upsample_bilinear2d: w_y0*(w_x0*a + w_x1*b) + w_y1*(w_x0*c + w_x1*d)
+    top = (img[:, y0][:, :, x0] * wx0[None, None, :] + img[:, y0][:, :, x1] * wx1[None, None, :]).astype(F32)
+    bot = (img[:, y1][:, :, x0] * wx0[None, None, :] + img[:, y1][:, :, x1] * wx1[None, None, :]).astype(F32)
+    return (wy0[None, :, None] * top + wy1[None, :, None] * bot).astype(F32)
+
+
 def decode(latent, frames, weights, times, scale=None, return_stages: bool = False,
-           chunk: int = 1 << 16):
-    """Restatement of ``LunaTokis.decoding(times, scale)``.
+           chunk: int = 1 << 16, upsampled_frames: bool = False):
+    """Restatement of ``LunaTokis.decoding(times, scale)``; with ``upsampled_frames`` of ``decoding_test`` (``:461-598``):
+    identical except that the frame pair is bilinearly upsampled x4 (``:513-514``) before every BILINEAR frame gather
+    (stage B ``:520-523``, stage D ``:548-551, :562-565``); the nearest gather of stage A still reads the LR frames
+    (``:486-489``), and ``scale`` is an integer factor there (``:467``).
 
     latent ``[B,3,64,H,W]`` (``self.feat``), frames ``[B,2,3,H,W]`` (``self.inp``), ``times`` ``[T]`` or
     ``[T,B]``, ``scale`` = None (x4) or the OUTPUT SIZE ``(HH, WW)`` (``:368-371``).
@@ -150,6 +176,8 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
     latent = np.asarray(latent, dtype=F32)
     frames = np.asarray(frames, dtype=F32)
     B, _, _, H, W = latent.shape
+    if upsampled_frames and scale is not None and np.ndim(scale) == 0:
+        scale = (H * int(scale), W * int(scale))
     HH, WW = (4 * H, 4 * W) if scale is None else (int(scale[0]), int(scale[1]))
     T = len(times)
     tm = _times_matrix(times, B)
@@ -163,6 +191,7 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
     for b in range(B):
         feat = latent[b].reshape(192, H, W)          # cat of self.feat[:,0..2] on channels (:365)
         fr = frames[b].reshape(6, H, W)              # self.inp.view(bs,-1,H,W)      (:387)
+        fr_bil = upsample4_bilinear(fr) if upsampled_frames else fr   # what the bilinear frame gathers sample
         # t-independent part of stage A / B (recomputed per timestep by the reference)
         iy, ix = ay["i"][jy], ax["i"][jx]
         ok = ((iy >= 0) & (iy < H) & (ix >= 0) & (ix < W)).astype(F32)[:, None]
@@ -189,7 +218,7 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
                 b_in = np.concatenate([
                     gather_nearest(hr_map, cy[s:e], cx[s:e]),                     # identity gather (:406-409)
                     gather_bilinear(feat, cy[s:e], cx[s:e]),                      # (:414-417)
-                    gather_bilinear(fr, cy[s:e], cx[s:e]),                        # (:410-413)
+                    gather_bilinear(fr_bil, cy[s:e], cx[s:e]),                    # (:410-413)
                     np.full((e - s, 1), t, dtype=F32)], axis=1).astype(F32)      # 263 (:418)
                 flow[s:e] = siren(b_in, weights, "flow_imnet")                    # (:419)
                 if s == 0:
@@ -208,7 +237,7 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
                 c_in = np.concatenate([
                     gather_bilinear(hr_map, y1, x1), gather_bilinear(hr_map, y2, x2),   # (:429-432,442-445)
                     gather_bilinear(feat, y1, x1), gather_bilinear(feat, y2, x2),       # (:437-440,450-453)
-                    gather_bilinear(fr, y1, x1), gather_bilinear(fr, y2, x2),           # (:433-436,446-449)
+                    gather_bilinear(fr_bil, y1, x1), gather_bilinear(fr_bil, y2, x2),   # (:433-436,446-449)
                     np.full((e - s, 1), t, dtype=F32)], axis=1).astype(F32)            # 525 (:455)
                 rgb[s:e] = siren(c_in, weights, "encode_imnet")                         # (:456)
                 if s == 0:
