@@ -51,6 +51,9 @@ extern "C" {
 #define STIF_MODE_FP32      1  /* fp32 FMA-pipe kernels; RGB within 1e-4 of the reference                           */
 /* flags OR-ed into `mode` */
 #define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085), either precision mode */
+#define STIF_FLAG_TEST_VARIANT   0x400  /* decoding_test semantics (Sakuya_arch_test.py:461-598, what VideoSRBaseModel.test runs):
+                                         * the frame pair is bilinearly upsampled x4 (:513-514) before every bilinear frame
+                                         * gather.  STIF_MODE_FP32 only in this build. */
 #define STIF_FLAG_OUT_U8         0x200  /* write what the reference's caller makes of the result (custom_video_test.py:102):
                                          * `(img.clamp(0,1).permute(1,2,0) * 255).astype(uint8)` -- uint8 [T,B,HH,WW,3],
                                          * fp32 clamp / multiply, truncation.  The `out` pointer is then a uint8_t buffer and

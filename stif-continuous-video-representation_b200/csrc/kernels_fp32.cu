@@ -133,8 +133,16 @@ __global__ void stage_a_first_layer(const float* __restrict__ tab, Geometry g, c
 // reference: Sakuya_arch_test.py:406-419.
 // f_table != null (local-ensemble pass): F is gathered at the nearest HR pixel of the SHIFTED coordinate
 // (Sakuya_arch_test.py:1026-1029) from the whole-slab table instead of being the query's own value.
+// pixel-centre query coordinate as make_coord builds it (Sakuya_arch_test.py:1233-1248 + clamp :373): two separately
+// rounded fp32 operations on double-derived constants
+__device__ __forceinline__ float query_coord(int j, int n) {
+  const float r0 = (float)(-1.0 + 1.0 / (double)n), step = (float)(2.0 / (double)n);
+  return fminf(fmaxf(__fadd_rn(r0, __fmul_rn(step, (float)j)), kClampLo), kClampHi);
+}
+
 __global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, Vec64 cst, long q0, long n,
-                                    float* __restrict__ f_inout, const float* __restrict__ f_table) {
+                                    float* __restrict__ f_inout, const float* __restrict__ f_table,
+                                    const float* __restrict__ utab) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 64) return;
   int c = (int)(i & 63);
@@ -144,6 +152,11 @@ __global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, V
   float s = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) s = fmaf(tp.w[k], tab[(long)tp.off[k] * 256 + 64 + c], s);
+  if (utab) {   // decoding_test: frames sampled bilinearly from the x4-upsampled pair at the query position (:520-523)
+    const Taps up = make_taps(query_coord(jy, g.HH), query_coord(jx, g.WW), 4 * g.H, 4 * g.W);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s = fmaf(up.w[k], utab[(long)up.off[k] * 192 + c], s);
+  }
   float f = f_inout[i];
   if (f_table) {
     const int hy = g.y.hidx[jy], hx = g.x.hidx[jx];
@@ -177,7 +190,8 @@ __global__ void ensemble_blend(const float* __restrict__ pred, float* __restrict
 // reference: warplayer.py:25-39, Sakuya_arch_test.py:424-456.
 __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* __restrict__ qtab,
                                     const float* __restrict__ flow, Geometry g, Vec64 cst, long q0, long n,
-                                    int band_lo, int band_hi, int* __restrict__ flag, float* __restrict__ out) {
+                                    int band_lo, int band_hi, int* __restrict__ flag, float* __restrict__ out,
+                                    const float* __restrict__ utab) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 64) return;
   int c = (int)(i & 63);
@@ -201,6 +215,11 @@ __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) s = fmaf(lr.w[k], tab[(long)lr.off[k] * 256 + 128 + wv * 64 + c], s);
+    if (utab) {   // decoding_test: frames at the warped position come from the x4-upsampled pair (:548-551, :562-565)
+      const Taps up = make_taps(gy, gx, 4 * g.H, 4 * g.W);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s = fmaf(up.w[k], utab[(long)up.off[k] * 192 + 64 + wv * 64 + c], s);
+    }
   }
   out[i] = sinf(s);
 }
@@ -247,11 +266,46 @@ cudaError_t rgb_to_u8_hwc(const LaunchCtx& cx, const float* rgb_planar, uint8_t*
   return cudaGetLastError();
 }
 
+// decoding_test variant: one thread per (texel of the 4H x 4W grid, output channel).  The six upsampled frame values are
+// ATen's upsample_bilinear2d (align_corners=False, scale 1/4): src = max(0, 0.25 (dst + 0.5) - 0.5), i1 = min(i0 + 1, n - 1),
+// value = wy0 (wx0 a + wx1 b) + wy1 (wx0 c + wx1 d), all in fp32 without contraction.
+__global__ void project_frames_up4_kernel(const float* __restrict__ frames, int H, int W, const float* __restrict__ w_up,
+                                          float* __restrict__ utab) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long n = (long)16 * H * W;
+  if (i >= n * 192) return;
+  const int c = (int)(i % 192);
+  const long texel = i / 192;
+  const int y = (int)(texel / (4 * W)), x = (int)(texel % (4 * W));
+  const float sy = fmaxf(0.f, __fadd_rn(__fmul_rn(0.25f, (float)y + 0.5f), -0.5f)), sx = fmaxf(0.f, __fadd_rn(__fmul_rn(0.25f, (float)x + 0.5f), -0.5f));
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = __fadd_rn(sy, -(float)y0), lx = __fadd_rn(sx, -(float)x0);
+  const float wy0 = __fadd_rn(1.f, -ly), wx0 = __fadd_rn(1.f, -lx);
+  float s = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 6; ++ch) {
+    const float* f = frames + (long)ch * H * W;
+    const float top = __fadd_rn(__fmul_rn(wx0, f[(long)y0 * W + x0]), __fmul_rn(lx, f[(long)y0 * W + x1]));
+    const float bot = __fadd_rn(__fmul_rn(wx0, f[(long)y1 * W + x0]), __fmul_rn(lx, f[(long)y1 * W + x1]));
+    const float v = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly, bot));
+    s = fmaf(w_up[c * 6 + ch], v, s);
+  }
+  utab[i] = s;
+}
+
+cudaError_t project_frames_up4(const LaunchCtx& cx, const DeviceWeights32& w, const float* frames6, int H, int W, float* utab) {
+  const long n = (long)16 * H * W * 192;
+  project_frames_up4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx.stream>>>(frames6, H, W, w.w_up, utab);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
 cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
-                           int H, int W, void* tab, bool tab_half) {
+                           int H, int W, void* tab, bool tab_half, bool test_variant) {
   GemmArgs g{};
   g.A = latent192; g.A2 = frames6; g.sam = 1; g.sak = (long)H * W; g.ksplit = 192;
-  g.Wt = w.w_tab; g.bias = nullptr; g.C = tab; g.scm = 256; g.scn = 1;
+  g.Wt = test_variant ? w.w_tab_lat : w.w_tab; g.bias = nullptr; g.C = tab; g.scm = 256; g.scn = 1;
   g.M = (long)H * W; g.N = 256; g.K = 198; g.act = 0; g.out_half = tab_half ? 1 : 0;
   return launch_gemm(cx, g, true);
 }
@@ -279,7 +333,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 64, 0), false));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
-    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr);
+    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr, ws.utab);
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
@@ -291,7 +345,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     long n = std::min(chunk, row_end * WW - q0);
     unsigned blocks = (unsigned)((n * 64 + 255) / 256);
     stage_e_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end,
-                                                      ws.flag, ws.act_c);
+                                                      ws.flag, ws.act_c, ws.utab);
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 64, 1), false));
@@ -340,7 +394,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
     for (long q0 = 0; q0 < Q; q0 += chunk) {
       long n = std::min(chunk, Q - q0);
       unsigned blocks = (unsigned)((n * 64 + 255) / 256);
-      stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, ws.ftab);
+      stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, ws.ftab, nullptr);
       ++*cx.launch_counter;
       STIF_TRY(cudaGetLastError());
       STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));

@@ -51,6 +51,15 @@ void fold_weights(const float* const* t, FoldedWeights& o) {
   put_cols(o.w_tab, 198, 128, 192, We0, 512, 518, kOmega);  //      frames@g1
   put_cols(o.w_tab, 198, 192, 0, We0, 320, 512, kOmega);    // TE2: latent@g2 ...
   put_cols(o.w_tab, 198, 192, 192, We0, 518, 524, kOmega);  //      frames@g2
+  // decoding_test variant: the bilinear frame gathers read the x4-upsampled pair, so the frame columns of TB | TE1 | TE2
+  // leave the LR table and become a [192,6] map applied on the 4H x 4W grid (TA keeps them: its gather is the LR nearest)
+  o.w_tab_lat = o.w_tab;
+  o.w_up.assign((size_t)192 * 6, 0.f);
+  for (int r = 64; r < 256; ++r)
+    for (int c = 0; c < 6; ++c) {
+      o.w_up[(size_t)(r - 64) * 6 + c] = o.w_tab[(size_t)r * 198 + 192 + c];
+      o.w_tab_lat[(size_t)r * 198 + 192 + c] = 0.f;
+    }
 
   o.a_rel.resize(128);
   for (int r = 0; r < 64; ++r) {

@@ -116,6 +116,7 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
   ws.flow = (float*)take(Q * 4 * sizeof(float));
   ws.flag = (int*)take(256);
   if (mode & STIF_FLAG_OUT_U8) ws.rgb32 = (float*)take(Q * 3 * sizeof(float));
+  if (mode & STIF_FLAG_TEST_VARIANT) ws.utab = (float*)take((size_t)16 * H * W * 192 * sizeof(float));
   if (fp32) {
     ws.chunk = std::min<size_t>(Q, (size_t)1 << 18);
     ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
@@ -435,6 +436,9 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   const int prec = mode & 0xFF;
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
   const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0, u8 = (mode & STIF_FLAG_OUT_U8) != 0;
+  const bool test_variant = (mode & STIF_FLAG_TEST_VARIANT) != 0;
+  if (test_variant && (prec != STIF_MODE_FP32 || ensemble))
+    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT is available with STIF_MODE_FP32 (without the ensemble flag) in this build");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
   if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
@@ -472,7 +476,10 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
       }
       ScopedSpan sp(d, stream, 0);
       if (prec == STIF_MODE_BF16) CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
-      else if (k == nbands - 1) CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false));
+      else if (k == nbands - 1) {
+        CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false, test_variant));
+        if (test_variant) CUDA_OR_RETURN(project_frames_up4(cx, d->w32, fr_b, H, W, ws.utab));
+      }
     }
     for (int c = 0; c < T; ++c) {
       const float t = times[(size_t)c * B + b];
@@ -584,7 +591,7 @@ int stif_load_weights(stif_decoder_t* d, const float* const* tensors, int num_te
   CUDA_OR_RETURN(cudaSetDevice(d->device));
   fold_weights(tensors, d->hw);
   const FoldedWeights& h = d->hw;
-  const std::vector<float>* parts[] = {&h.w_tab, &h.a_rel, &h.a_t, &h.a_b, &h.f1_w, &h.f1_b, &h.f2_w, &h.f2_b, &h.f3_w, &h.f3_b,
+  const std::vector<float>* parts[] = {&h.w_tab, &h.w_tab_lat, &h.w_up, &h.a_rel, &h.a_t, &h.a_b, &h.f1_w, &h.f1_b, &h.f2_w, &h.f2_b, &h.f3_w, &h.f3_b,
                                        &h.b_t, &h.b_b, &h.l1_w, &h.l1_b, &h.l2_w, &h.l2_b, &h.l3_w, &h.l3_b,
                                        &h.e_t, &h.e_b, &h.e1_w, &h.e1_b, &h.e2_w, &h.e2_b, &h.e3_w, &h.e3_b, &h.e4_w, &h.e4_b};
   constexpr int NP = sizeof(parts) / sizeof(parts[0]);
@@ -595,7 +602,7 @@ int stif_load_weights(stif_decoder_t* d, const float* const* tensors, int num_te
   if (d->d_w32) { cudaFree(d->d_w32); d->d_w32 = nullptr; }
   CUDA_OR_RETURN(cudaMalloc(&d->d_w32, total * sizeof(float)));
   CUDA_OR_RETURN(cudaMemcpy(d->d_w32, host.data(), total * sizeof(float), cudaMemcpyHostToDevice));
-  const float** fields[] = {&d->w32.w_tab, &d->w32.a_rel, &d->w32.a_t, &d->w32.a_b, &d->w32.f1_w, &d->w32.f1_b, &d->w32.f2_w,
+  const float** fields[] = {&d->w32.w_tab, &d->w32.w_tab_lat, &d->w32.w_up, &d->w32.a_rel, &d->w32.a_t, &d->w32.a_b, &d->w32.f1_w, &d->w32.f1_b, &d->w32.f2_w,
                             &d->w32.f2_b, &d->w32.f3_w, &d->w32.f3_b, &d->w32.b_t, &d->w32.b_b, &d->w32.l1_w, &d->w32.l1_b,
                             &d->w32.l2_w, &d->w32.l2_b, &d->w32.l3_w, &d->w32.l3_b, &d->w32.e_t, &d->w32.e_b, &d->w32.e1_w,
                             &d->w32.e1_b, &d->w32.e2_w, &d->w32.e2_b, &d->w32.e3_w, &d->w32.e3_b, &d->w32.e4_w, &d->w32.e4_b};

@@ -16,6 +16,8 @@ namespace stif {
 // are composed with feat_imnet's last linear layer.  All fp32, row-major [out,in].
 struct FoldedWeights {
   std::vector<float> w_tab;          // [256,198]  rows: TA | TB | TE1 | TE2 ; cols: latent(192), frames(6)
+  std::vector<float> w_tab_lat;      // decoding_test variant: same, frame columns of TB | TE1 | TE2 zeroed (they move to w_up)
+  std::vector<float> w_up;           // decoding_test variant: [192,6] frame columns of TB | TE1 | TE2, applied to the x4-upsampled frames
   std::vector<float> a_rel;          // [64,2]     (rely, relx) columns of feat_imnet layer 0
   std::vector<float> a_t, a_b;       // [64]       t column / bias of feat_imnet layer 0
   std::vector<float> f1_w, f1_b;     // [64,64]
@@ -37,7 +39,7 @@ void fold_weights(const float* const* tensors, FoldedWeights& out);
 
 // Device-side view of the fp32 copy (kernels_fp32.cu).
 struct DeviceWeights32 {
-  const float *w_tab, *a_rel, *a_t, *a_b, *f1_w, *f1_b, *f2_w, *f2_b, *f3_w, *f3_b;
+  const float *w_tab, *w_tab_lat, *w_up, *a_rel, *a_t, *a_b, *f1_w, *f1_b, *f2_w, *f2_b, *f3_w, *f3_b;
   const float *b_t, *b_b, *l1_w, *l1_b, *l2_w, *l2_b, *l3_w, *l3_b;
   const float *e_t, *e_b, *e1_w, *e1_b, *e2_w, *e2_b, *e3_w, *e3_b, *e4_w, *e4_b;
 };
@@ -73,6 +75,7 @@ struct Workspace {
   float* ftab;    // local-ensemble mode: F = 30 Wl0[:, :64] HRfeat for the whole slab [HH*WW,64]
   float* pred;    // local-ensemble mode: one pass's prediction [3,HH*WW]
   int* flag;      // device int: row-band halo violation flag
+  float* utab;    // STIF_FLAG_TEST_VARIANT: [4H*4W,192] fp32 UB | UE1 | UE2 = frame columns applied to the x4-upsampled frames
   float* rgb32;   // STIF_FLAG_OUT_U8: fp32 staging of one slab [3,HH*WW] ahead of the uint8 conversion
   size_t chunk;   // queries per activation chunk (FP32 mode)
   size_t total_bytes;
@@ -80,8 +83,10 @@ struct Workspace {
 Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode);
 
 // fp32 FMA-pipe path (kernels_fp32.cu)
+// decoding_test variant (Sakuya_arch_test.py:513-514): utab[4H*4W,192] = w_up . bilinear_upsample_x4(frames)
+cudaError_t project_frames_up4(const LaunchCtx& cx, const DeviceWeights32& w, const float* frames6, int H, int W, float* utab);
 cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
-                           int H, int W, void* tab, bool tab_half);
+                           int H, int W, void* tab, bool tab_half, bool test_variant = false);
 cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
                              const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
                              int k1_row_end, float* out_rgb /* [3,HH,WW] */, int stage /* 1 = K1 (A+B), 2 = K2 (C+D+E) */);

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import STIF_FLAG_LOCAL_ENSEMBLE, STIF_FLAG_OUT_U8, STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
+from ._lib import STIF_FLAG_LOCAL_ENSEMBLE, STIF_FLAG_OUT_U8, STIF_FLAG_TEST_VARIANT, STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
 
 _MODES = {"bf16": STIF_MODE_BF16, "fp32": STIF_MODE_FP32}
 
@@ -148,7 +148,8 @@ class STIFQueryDecoder(torch.nn.Module):
 
     def decode_stacked(self, latent, frames, times, scale=None, mode: str | None = None,
                        rows: tuple[int, int] | None = None, halo: int = 0,
-                       out: torch.Tensor | None = None, local_ensemble: bool = False, uint8: bool = False) -> torch.Tensor:
+                       out: torch.Tensor | None = None, local_ensemble: bool = False, uint8: bool = False,
+                       test_variant: bool = False) -> torch.Tensor:
         """Decode to one ``[T,B,3,HH,WW]`` fp32 tensor.  ``rows=(r0,r1)`` restricts the call to a row band
         (``stif_decode_rows``), used by the sharding launcher.  ``uint8=True`` returns what the reference's caller
         saves (``custom_video_test.py:102``): ``(clamp(0,1) * 255).astype(uint8)`` as ``[T,B,HH,WW,3]``."""
@@ -157,7 +158,8 @@ class STIFQueryDecoder(torch.nn.Module):
         latent, frames, B, H, W, HH, WW = self._prep(latent, frames, scale)
         tm = _times_matrix(times, B)
         T = tm.shape[0]
-        m = _MODES[mode or self.mode] | (STIF_FLAG_LOCAL_ENSEMBLE if local_ensemble else 0) | (STIF_FLAG_OUT_U8 if uint8 else 0)
+        m = (_MODES[mode or self.mode] | (STIF_FLAG_LOCAL_ENSEMBLE if local_ensemble else 0) | (STIF_FLAG_OUT_U8 if uint8 else 0)
+             | (STIF_FLAG_TEST_VARIANT if test_variant else 0))
         ws = self._workspace_for(B, H, W, HH, WW, T, m)
         shape, dtype = ((T, B, HH, WW, 3), torch.uint8) if uint8 else ((T, B, 3, HH, WW), torch.float32)
         if out is None:
@@ -179,6 +181,14 @@ class STIFQueryDecoder(torch.nn.Module):
     def decode(self, latent, frames, times, scale=None, mode: str | None = None) -> list[torch.Tensor]:
         """``LunaTokis.decoding`` return convention: list of ``T`` tensors ``[B,3,HH,WW]``."""
         return list(self.decode_stacked(latent, frames, times, scale, mode).unbind(0))
+
+    def decode_test(self, latent, frames, times, scale=None) -> list[torch.Tensor]:
+        """``LunaTokis.decoding_test`` (``Sakuya_arch_test.py:461-598``, what ``VideoSRBaseModel.test`` runs): as ``decode`` but
+        the bilinear frame gathers read the x4-upsampled frame pair.  ``scale`` is the reference's integer factor
+        (``:467``) or, as the shipped evaluation loops pass it, an output size tuple.  fp32 kernels in this build."""
+        if scale is not None and not isinstance(scale, (tuple, list)):
+            scale = (int(latent.shape[-2]) * int(scale), int(latent.shape[-1]) * int(scale))
+        return list(self.decode_stacked(latent, frames, times, scale, mode="fp32", test_variant=True).unbind(0))
 
     def decode_localensemble(self, latent, frames, times, scale=None, mode: str | None = None) -> torch.Tensor:
         """``LunaTokis.decoding_localensemble`` (``Sakuya_arch_test.py:962-1085``): four shifted passes blended by
@@ -319,6 +329,7 @@ def patch_reference_model(model, mode: str = "bf16"):
     model.decoding = decoding
     model.decoding_fasttest = decoding_fasttest
     model.decoding_localensemble = lambda times=None, scale=None: dec.decode_localensemble(model.feat, model.inp, times, scale)
+    model.decoding_test = lambda times=None, scale=None: dec.decode_test(model.feat, model.inp, times, scale)
     model.decoding_fasttest_memory = decoding_fasttest
     model.stif_decoder = dec
     model.stif_refresh_weights = lambda: dec.load_weights(_decoder_state(model))

@@ -12,7 +12,7 @@ import torch
 from conftest import GOLD
 from oracle import port_torch, synth
 from oracle import restate_np as R
-from oracle.make_goldens import CASES
+from oracle.make_goldens import CASES, TEST_VARIANT_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -340,3 +340,27 @@ def test_uint8_host_pipeline_banded(stif):
     want = _to_u8_like_reference(_run(dec, lat, fr, times, (384, 163)))
     dec.host_pipeline(bands=5, halo=16)
     assert np.array_equal(dec.decode_host(lat, fr, times, (384, 163), uint8=True).numpy(), want)
+
+
+@pytest.mark.parametrize("name", list(TEST_VARIANT_CASES))
+def test_decoding_test_variant(name, decoders):
+    """STIF_FLAG_TEST_VARIANT = `LunaTokis.decoding_test` (Sakuya_arch_test.py:461-598): the bilinear frame gathers read
+    the x4-upsampled frame pair.  fp32 kernels against the reference's own run (int scale as the method takes it, and the
+    equivalent output-size tuple the shipped eval loops pass), flow included."""
+    cfg = TEST_VARIANT_CASES[name]
+    g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+    lat, fr = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    dec = decoders(cfg["wseed"], cfg["stress"], "fp32")
+    L, F = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    out = torch.stack(dec.decode_test(L, F, cfg["times"], cfg["scale"]), 0)
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - g["rgb"]).max()
+    flow_err = np.abs(dec.last_flow(out.shape[-2], out.shape[-1]) - g["flow"][-1]).max()
+    print(f"{name}: decoding_test rgb max-abs {err:.3e}, flow max-abs {flow_err:.3e}")
+    assert err <= 1e-4 and flow_err <= 1e-3
+    if cfg["scale"] is not None:
+        size = (cfg["H"] * cfg["scale"], cfg["W"] * cfg["scale"])
+        again = torch.stack(dec.decode_test(L, F, cfg["times"], size), 0)
+        assert torch.equal(again, out)
+    plain = torch.stack(dec.decode(L, F, cfg["times"], None if cfg["scale"] is None else size), 0)
+    assert float((plain - out).abs().max()) > 1e-3        # a different function from `decoding`
