@@ -246,8 +246,10 @@ __global__ void rgb_to_u8_hwc_kernel(const float* __restrict__ rgb, uint8_t* __r
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[3 * i + c] = (uint8_t)(fminf(fmaxf(__ldg(rgb + c * Q + q), 0.f), 1.f) * 255.f);
   }
-  if (q0 >= q_begin && q0 + 3 < q_end) {
-    uint32_t* o = reinterpret_cast<uint32_t*>(out + q0 * 3);   // q0 % 4 == 0 -> 12-byte aligned run, 4-byte aligned words
+  // word stores need 4-byte alignment of the absolute address: the 12-byte run starts at a multiple of 12 bytes inside
+  // the slab, but the slab itself starts at slab_index * 3 * HH * WW bytes, which is odd-sized for odd rasters
+  if (q0 >= q_begin && q0 + 3 < q_end && (reinterpret_cast<uintptr_t>(out + q0 * 3) & 3) == 0) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + q0 * 3);
 #pragma unroll
     for (int w = 0; w < 3; ++w) o[w] = v[4 * w] | (v[4 * w + 1] << 8) | (v[4 * w + 2] << 16) | ((uint32_t)v[4 * w + 3] << 24);
   } else {
