@@ -404,3 +404,39 @@ def test_random_shapes_fuzz(stif):
         u8 = bf.decode_stacked(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), _times(times), (HH, WW), uint8=True)
         assert np.array_equal(u8.cpu().numpy(), _to_u8_like_reference(a)), (H, W, HH, WW)
     print(f"fuzz: worst bf16-vs-fp32 max-abs {worst:.3e} over 24 geometries")
+
+
+def test_random_shapes_fuzz_modes(stif):
+    """Second seeded sweep: the local-ensemble mode (tensor-core vs fp32 kernels) and the band-major host pipeline with
+    forced band counts / tiny halos on mid-size rasters (speculation misses included) -- results must not depend on them."""
+    rng = np.random.default_rng(77)
+    bf = stif.STIFQueryDecoder(0, mode="bf16")
+    fp = stif.STIFQueryDecoder(0, mode="fp32")
+    w = synth.make_weights(4, True)
+    bf.load_weights(w)
+    fp.load_weights(w)
+    worst = 0.0
+    for it in range(8):
+        H, W = int(rng.integers(8, 48)), int(rng.integers(8, 48))
+        HH, WW = int(rng.integers(2 * H, 5 * H)), int(rng.integers(2 * W, 5 * W))
+        lat, fr = synth.make_inputs(2000 + it, 1, H, W, 0.3)
+        L, F = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+        times = [float(t) for t in rng.random(int(rng.integers(1, 4)))]
+        a = bf.decode_localensemble(L, F, times, (HH, WW))
+        b = fp.decode_localensemble(L, F, times, (HH, WW))
+        err = float((a - b).abs().max())
+        worst = max(worst, err)
+        assert err <= 2e-2, (H, W, HH, WW, err)
+    misses = 0
+    for it in range(8):
+        H, W = int(rng.integers(40, 120)), int(rng.integers(20, 90))
+        HH, WW = int(rng.integers(2 * H, 5 * H)), int(rng.integers(2 * W, 5 * W))
+        T = int(rng.integers(1, 7))
+        lat, fr = synth.make_inputs(3000 + it, 1, H, W, float(rng.choice([0.05, 1.0])))
+        times = [float(t) for t in rng.random(T)]
+        ref = _run(bf, lat, fr, times, (HH, WW))
+        before = bf.host_pipeline(bands=int(rng.integers(2, 9)), halo=int(rng.choice([1, 4, 16, 64])))
+        host = bf.decode_host(lat, fr, times, (HH, WW)).numpy()
+        misses += bf.host_pipeline() - before
+        assert np.array_equal(host, ref), (H, W, HH, WW, T)
+    print(f"fuzz modes: worst ensemble bf16-vs-fp32 {worst:.3e}; host pipeline speculation misses repaired: {misses}")
