@@ -45,11 +45,13 @@ def _siren(x: torch.Tensor, w: dict, net: str) -> torch.Tensor:
 
 
 @torch.no_grad()
-def decode(latent, frames, weights, times, scale=None) -> torch.Tensor:
-    """latent [B,3,64,H,W], frames [B,2,3,H,W], times [T] or [T,B] -> rgb [T,B,3,HH,WW] (torch CPU fp32)."""
-    latent = torch.as_tensor(latent, dtype=torch.float32)
-    frames = torch.as_tensor(frames, dtype=torch.float32)
-    w = {k: torch.as_tensor(v, dtype=torch.float32) for k, v in weights.items()}
+def decode(latent, frames, weights, times, scale=None, device: str = "cpu") -> torch.Tensor:
+    """latent [B,3,64,H,W], frames [B,2,3,H,W], times [T] or [T,B] -> rgb [T,B,3,HH,WW] (torch fp32).  ``device`` = "cpu"
+    for the timed CPU baseline; "cuda" runs the SAME eager op sequence on the GPU (``profiles/eager_gpu_baseline.py``:
+    the reference's own execution model on the same box)."""
+    latent = torch.as_tensor(latent, dtype=torch.float32).to(device)
+    frames = torch.as_tensor(frames, dtype=torch.float32).to(device)
+    w = {k: torch.as_tensor(v, dtype=torch.float32).to(device) for k, v in weights.items()}
     B, _, _, H, W = latent.shape
     feat = latent.reshape(B, 192, H, W)
     inp6 = frames.reshape(B, 6, H, W)
@@ -58,14 +60,14 @@ def decode(latent, frames, weights, times, scale=None) -> torch.Tensor:
     tm = np.asarray(times, dtype=np.float32)
     if tm.ndim == 1:
         tm = np.repeat(tm[:, None], B, 1)
-    coord = _grid(HH, WW).unsqueeze(0).repeat(B, 1, 1).clamp(-1 + _EPS, 1 - _EPS)      # (:373)
-    lr = _grid(H, W).view(H, W, 2).permute(2, 0, 1).unsqueeze(0).expand(B, 2, H, W)    # (:375-377)
-    bx = torch.linspace(-1.0, 1.0, WW).view(1, 1, WW).expand(B, HH, WW)                # warplayer.py:28-31
-    by = torch.linspace(-1.0, 1.0, HH).view(1, HH, 1).expand(B, HH, WW)
+    coord = _grid(HH, WW).unsqueeze(0).repeat(B, 1, 1).clamp(-1 + _EPS, 1 - _EPS).to(device)      # (:373)
+    lr = _grid(H, W).view(H, W, 2).permute(2, 0, 1).unsqueeze(0).expand(B, 2, H, W).to(device)    # (:375-377)
+    bx = torch.linspace(-1.0, 1.0, WW).view(1, 1, WW).expand(B, HH, WW).to(device)                # warplayer.py:28-31
+    by = torch.linspace(-1.0, 1.0, HH).view(1, HH, 1).expand(B, HH, WW).to(device)
     outs = []
     for c in range(tm.shape[0]):
-        t = torch.from_numpy(tm[c]).view(B, 1, 1)
-        pe = torch.ones(B, Q, 1) * t
+        t = torch.from_numpy(tm[c]).view(B, 1, 1).to(device)
+        pe = torch.ones(B, Q, 1, device=device) * t
         # stage A (:382-401)
         q_feat = _sample(feat, coord, "nearest")
         q_inp = _sample(inp6, coord, "nearest")
