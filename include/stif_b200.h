@@ -54,6 +54,10 @@ extern "C" {
 #define STIF_FLAG_TEST_VARIANT   0x400  /* decoding_test semantics (Sakuya_arch_test.py:461-598, what VideoSRBaseModel.test runs):
                                          * the frame pair is bilinearly upsampled x4 (:513-514) before every bilinear frame
                                          * gather.  STIF_MODE_FP32 only in this build. */
+#define STIF_FLAG_WARP_FROM_COORD 0x800 /* warpgrid2 semantics (warplayer.py:41-47): the warp starts from the query's own
+                                         * pixel-centre coordinate instead of the linspace base grid.  Together with
+                                         * STIF_FLAG_TEST_VARIANT and stif_decode_rows this is decoding_memory
+                                         * (Sakuya_arch_test.py:600-861) without its file-system side effects.  FP32 only. */
 #define STIF_FLAG_OUT_U8         0x200  /* write what the reference's caller makes of the result (custom_video_test.py:102):
                                          * `(img.clamp(0,1).permute(1,2,0) * 255).astype(uint8)` -- uint8 [T,B,HH,WW,3],
                                          * fp32 clamp / multiply, truncation.  The `out` pointer is then a uint8_t buffer and

@@ -154,6 +154,58 @@ def run_test_variant(cfg: dict) -> dict:
             "input_checksum": np.float64(checksum(latent, frames)), "weight_checksum": np.float64(checksum(*weights.values()))}
 
 
+MEMORY_VARIANT_CASES = {
+    # decoding_memory (Sakuya_arch_test.py:600-861): stage A on the full (HH,WW) raster, stages B-E (decoding_test's upsampled
+    # frames, warpgrid2) on a 4H x 4W window around `center`; the window is clamped into the raster
+    "memvar_mid": dict(H=12, W=10, scale=(100, 90), center=(0.1, -0.2), times=[0.3, 0.9], wseed=1, stress=True, iseed=3, latent_std=0.3),
+    "memvar_corner": dict(H=8, W=9, scale=(40, 50), center=(-0.9, 0.8), times=[0.5], wseed=2, stress=True, iseed=4, latent_std=1.0),
+}
+
+
+def window_of(H, W, HH, WW, center):
+    """Rows [x0,x1) and columns [y0,y1) of the window, exactly as the method computes them (:636-650)."""
+    H0, W0 = 4 * H, 4 * W
+    cc = ((np.asarray(center, dtype=np.float64) + 1) / 2) * np.array((HH, WW))
+    x0, x1, y0, y1 = int(cc[0]) - H0 // 2, int(cc[0]) + H0 - H0 // 2, int(cc[1]) - W0 // 2, int(cc[1]) + W0 - W0 // 2
+    if x0 < 0:
+        x1 -= x0
+        x0 = 0
+    elif x1 > HH:
+        x0 -= (x1 - HH)
+        x1 = HH
+    if y0 < 0:
+        y1 -= y0
+        y0 = 0
+    elif y1 > WW:
+        y0 -= (y1 - WW)
+        y1 = WW
+    return x0, x1, y0, y1
+
+
+def run_memory_variant(cfg: dict) -> dict:
+    """`LunaTokis.decoding_memory(times, scale, center, input_img)` with its file-system side effects (hard-coded
+    `/home/users/...` directories, JPEG saves, :609-651) neutralised for the duration of the call -- nothing outside the
+    numerical path is touched."""
+    import os as _os
+    import torch
+    from unittest import mock
+    from PIL import Image
+
+    weights = synth.make_weights(cfg["wseed"], cfg["stress"])
+    latent, frames = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    model = build_reference_model(weights)
+    clear_warp_cache()
+    model.feat = torch.from_numpy(latent)
+    model.inp = torch.from_numpy(frames)
+    times = [torch.tensor([[float(t)]], dtype=torch.float32) for t in cfg["times"]]
+    with mock.patch.object(_os, "makedirs", lambda *a, **k: None), mock.patch.object(_os.path, "exists", lambda p: True), \
+            mock.patch.object(Image.Image, "save", lambda self, *a, **k: None), torch.no_grad():
+        preds = model.decoding_memory(times, cfg["scale"], np.asarray(cfg["center"], dtype=np.float64), torch.from_numpy(frames))
+    x0, x1, y0, y1 = window_of(cfg["H"], cfg["W"], cfg["scale"][0], cfg["scale"][1], cfg["center"])
+    return {"rgb": np.stack([p.numpy() for p in preds], 0).astype(np.float32), "window": np.asarray([x0, x1, y0, y1], dtype=np.int64),
+            "input_checksum": np.float64(checksum(latent, frames)), "weight_checksum": np.float64(checksum(*weights.values()))}
+
+
 def run_config1(stress: bool) -> dict:
     """Config 1 of BASELINE.json (64x64 latent -> 256x256, 8 timesteps): store a strided sample."""
     import torch
@@ -241,6 +293,10 @@ def main():
         res = run_test_variant(cfg)
         np.savez_compressed(os.path.join(GOLD, f"case_{name}.npz"), **res)
         print(name, res["rgb"].shape)
+    for name, cfg in MEMORY_VARIANT_CASES.items():
+        res = run_memory_variant(cfg)
+        np.savez_compressed(os.path.join(GOLD, f"case_{name}.npz"), **res)
+        print(name, res["rgb"].shape, res["window"])
     np.savez_compressed(os.path.join(GOLD, "e2e_small.npz"), **run_e2e_small())
     np.savez_compressed(os.path.join(GOLD, "axis_tables.npz"), **axis_goldens())
     print("done")

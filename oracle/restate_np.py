@@ -163,11 +163,14 @@ def upsample4_bilinear(img: np.ndarray) -> np.ndarray:
 
 
 def decode(latent, frames, weights, times, scale=None, return_stages: bool = False,
-           chunk: int = 1 << 16, upsampled_frames: bool = False):
+           chunk: int = 1 << 16, upsampled_frames: bool = False, window=None):
     """Restatement of ``LunaTokis.decoding(times, scale)``; with ``upsampled_frames`` of ``decoding_test`` (``:461-598``):
     identical except that the frame pair is bilinearly upsampled x4 (``:513-514``) before every BILINEAR frame gather
     (stage B ``:520-523``, stage D ``:548-551, :562-565``); the nearest gather of stage A still reads the LR frames
     (``:486-489``), and ``scale`` is an integer factor there (``:467``).
+    ``window = (x0, x1, y0, y1)`` (rows, columns) gives ``decoding_memory`` (``:600-861``): stage A on the whole raster,
+    stages B-E of ``decoding_test`` on the window only, with ``warpgrid2`` (``warplayer.py:41-47``: the warp starts from the
+    query's pixel-centre coordinate instead of the linspace base grid); the result is ``[T,B,3,x1-x0,y1-y0]``.
 
     latent ``[B,3,64,H,W]`` (``self.feat``), frames ``[B,2,3,H,W]`` (``self.inp``), ``times`` ``[T]`` or
     ``[T,B]``, ``scale`` = None (x4) or the OUTPUT SIZE ``(HH, WW)`` (``:368-371``).
@@ -186,7 +189,15 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
     Q = HH * WW
     jy, jx = np.divmod(np.arange(Q), WW)
     cy, cx = ay["c"][jy], ax["c"][jx]
-    out = np.zeros((T, B, 3, HH, WW), dtype=F32)
+    if window is not None:
+        x0, x1, y0, y1 = (int(v) for v in window)
+        sel = (np.arange(x0, x1)[:, None] * WW + np.arange(y0, y1)[None, :]).ravel()     # stages B-E see these queries only
+        out_h, out_w = x1 - x0, y1 - y0
+    else:
+        sel, out_h, out_w = np.arange(Q), HH, WW
+    QS = sel.size
+    sjy, sjx, scy, scx = jy[sel], jx[sel], cy[sel], cx[sel]
+    out = np.zeros((T, B, 3, out_h, out_w), dtype=F32)
     stages = {}
     for b in range(B):
         feat = latent[b].reshape(192, H, W)          # cat of self.feat[:,0..2] on channels (:365)
@@ -211,28 +222,30 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
                 if s == 0:
                     a_in_keep = a_in
             hr_map = np.ascontiguousarray(hr.T).reshape(64, HH, WW)               # (:401)
-            flow = np.zeros((Q, 4), dtype=F32)
+            flow = np.zeros((QS, 4), dtype=F32)
             b_in_keep = None
-            for s in range(0, Q, chunk):
-                e = min(Q, s + chunk)
+            for s in range(0, QS, chunk):
+                e = min(QS, s + chunk)
                 b_in = np.concatenate([
-                    gather_nearest(hr_map, cy[s:e], cx[s:e]),                     # identity gather (:406-409)
-                    gather_bilinear(feat, cy[s:e], cx[s:e]),                      # (:414-417)
-                    gather_bilinear(fr_bil, cy[s:e], cx[s:e]),                    # (:410-413)
+                    gather_nearest(hr_map, scy[s:e], scx[s:e]),                   # identity gather (:406-409)
+                    gather_bilinear(feat, scy[s:e], scx[s:e]),                    # (:414-417)
+                    gather_bilinear(fr_bil, scy[s:e], scx[s:e]),                  # (:410-413)
                     np.full((e - s, 1), t, dtype=F32)], axis=1).astype(F32)      # 263 (:418)
                 flow[s:e] = siren(b_in, weights, "flow_imnet")                    # (:419)
                 if s == 0:
                     b_in_keep = b_in
             # stage C: warpgrid (warplayer.py:25-39); flow ch0/1 = (dx,dy) to frame 0, ch2/3 to frame 1
-            gx1 = (ax["base"][jx] + flow[:, 0] / F32((WW - 1.0) / 2.0)).astype(F32)
-            gy1 = (ay["base"][jy] + flow[:, 1] / F32((HH - 1.0) / 2.0)).astype(F32)
-            gx2 = (ax["base"][jx] + flow[:, 2] / F32((WW - 1.0) / 2.0)).astype(F32)
-            gy2 = (ay["base"][jy] + flow[:, 3] / F32((HH - 1.0) / 2.0)).astype(F32)
+            # (decoding_memory: warpgrid2 starts from the query coordinate itself, warplayer.py:41-47)
+            bx_, by_ = (scx, scy) if window is not None else (ax["base"][sjx], ay["base"][sjy])
+            gx1 = (bx_ + flow[:, 0] / F32((WW - 1.0) / 2.0)).astype(F32)
+            gy1 = (by_ + flow[:, 1] / F32((HH - 1.0) / 2.0)).astype(F32)
+            gx2 = (bx_ + flow[:, 2] / F32((WW - 1.0) / 2.0)).astype(F32)
+            gy2 = (by_ + flow[:, 3] / F32((HH - 1.0) / 2.0)).astype(F32)
             gx1, gy1, gx2, gy2 = (clamp_axis(g) for g in (gx1, gy1, gx2, gy2))   # (:428,441)
-            rgb = np.zeros((Q, 3), dtype=F32)
+            rgb = np.zeros((QS, 3), dtype=F32)
             c_in_keep = None
-            for s in range(0, Q, chunk):
-                e = min(Q, s + chunk)
+            for s in range(0, QS, chunk):
+                e = min(QS, s + chunk)
                 y1, x1, y2, x2 = gy1[s:e], gx1[s:e], gy2[s:e], gx2[s:e]
                 c_in = np.concatenate([
                     gather_bilinear(hr_map, y1, x1), gather_bilinear(hr_map, y2, x2),   # (:429-432,442-445)
@@ -242,7 +255,7 @@ def decode(latent, frames, weights, times, scale=None, return_stages: bool = Fal
                 rgb[s:e] = siren(c_in, weights, "encode_imnet")                         # (:456)
                 if s == 0:
                     c_in_keep = c_in
-            out[c, b] = rgb.T.reshape(3, HH, WW)                                         # (:457)
+            out[c, b] = rgb.T.reshape(3, out_h, out_w)                                   # (:457)
             if return_stages:
                 stages = {"feat_in": a_in_keep, "hr": hr, "flow_in": b_in_keep, "flow": flow,
                           "grid1": np.stack([gy1, gx1], 1), "grid2": np.stack([gy2, gx2], 1),

@@ -78,7 +78,7 @@ struct stif_decoder {
   float* d_w32 = nullptr;  // fp32 folded weights (one allocation)
   DeviceWeights32 w32{};
   TcWeights* tcw = nullptr;
-  std::map<std::array<int, 4>, DeviceGeometry> geos;
+  std::map<std::array<int, 5>, DeviceGeometry> geos;   // key: H, W, HH, WW, warp-base variant
   int64_t launches = 0;
   // last decoded slab (debug introspection)
   const float* last_flow = nullptr;
@@ -149,13 +149,16 @@ int check_shape(int B, int H, int W, int HH, int WW, int T) {
   return STIF_OK;
 }
 
-int get_geometry(stif_decoder* d, int H, int W, int HH, int WW, cudaStream_t stream, const Geometry** out) {
-  std::array<int, 4> key{H, W, HH, WW};
+// warp_from_coord: the warp base grid is the query's pixel-centre coordinate (warpgrid2, warplayer.py:41-47) instead of
+// torch.linspace(-1, 1, n) (warpgrid, :28-31) -- the only thing decoding_memory's stage C does differently
+int get_geometry(stif_decoder* d, int H, int W, int HH, int WW, cudaStream_t stream, const Geometry** out, bool warp_from_coord = false) {
+  std::array<int, 5> key{H, W, HH, WW, warp_from_coord ? 1 : 0};
   auto it = d->geos.find(key);
   if (it == d->geos.end()) {
     HostAxis ay, ax;
     build_axis(H, HH, ay);
     build_axis(W, WW, ax);
+    if (warp_from_coord) { ay.base = ay.coord; ax.base = ax.coord; }
     // blob layout: y{idx,rel,b0,bw,base} x{idx,rel,b0,bw,base}, each 256-byte aligned
     size_t ny = align256((size_t)HH * 4), nx = align256((size_t)WW * 4);
     size_t total = 5 * ny + 5 * nx;
@@ -197,7 +200,7 @@ int get_geometry(stif_decoder* d, int H, int W, int HH, int WW, cudaStream_t str
 int get_ensemble_geometry(stif_decoder* d, int H, int W, int HH, int WW, DeviceGeometry** out) {
   const Geometry* base = nullptr;
   if (int rc = get_geometry(d, H, W, HH, WW, nullptr, &base)) return rc;
-  DeviceGeometry& dg = d->geos.find(std::array<int, 4>{H, W, HH, WW})->second;
+  DeviceGeometry& dg = d->geos.find(std::array<int, 5>{H, W, HH, WW, 0})->second;
   if (!dg.has_ensemble) {
     for (int s = 0; s < 2; ++s) {
       HostAxis ay, ax;
@@ -436,9 +439,9 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   const int prec = mode & 0xFF;
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
   const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0, u8 = (mode & STIF_FLAG_OUT_U8) != 0;
-  const bool test_variant = (mode & STIF_FLAG_TEST_VARIANT) != 0;
-  if (test_variant && (prec != STIF_MODE_FP32 || ensemble))
-    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT is available with STIF_MODE_FP32 (without the ensemble flag) in this build");
+  const bool test_variant = (mode & STIF_FLAG_TEST_VARIANT) != 0, warp_from_coord = (mode & STIF_FLAG_WARP_FROM_COORD) != 0;
+  if ((test_variant || warp_from_coord) && (prec != STIF_MODE_FP32 || ensemble))
+    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT / STIF_FLAG_WARP_FROM_COORD are available with STIF_MODE_FP32 (without the ensemble flag) in this build");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
   if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
@@ -449,7 +452,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   CUDA_OR_RETURN(cudaSetDevice(d->device));
   if (hp && prec == STIF_MODE_BF16 && !ensemble) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
   const Geometry* geo = nullptr;
-  if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo)) return rc;
+  if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo, warp_from_coord)) return rc;
   Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
   LaunchCtx cx{stream, &d->launches, d->num_sms};
   const int k1_lo = std::max(0, row_begin - halo), k1_hi = std::min(HH, row_end + halo);

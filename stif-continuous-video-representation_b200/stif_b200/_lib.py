@@ -17,6 +17,7 @@ STIF_MODE_FP32 = 1
 STIF_FLAG_LOCAL_ENSEMBLE = 0x100
 STIF_FLAG_OUT_U8 = 0x200
 STIF_FLAG_TEST_VARIANT = 0x400
+STIF_FLAG_WARP_FROM_COORD = 0x800
 STIF_NUM_WEIGHT_TENSORS = 26
 STIF_ABI_VERSION = 1
 

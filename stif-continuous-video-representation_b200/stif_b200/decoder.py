@@ -23,7 +23,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import STIF_FLAG_LOCAL_ENSEMBLE, STIF_FLAG_OUT_U8, STIF_FLAG_TEST_VARIANT, STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib
+from ._lib import (STIF_FLAG_LOCAL_ENSEMBLE, STIF_FLAG_OUT_U8, STIF_FLAG_TEST_VARIANT, STIF_FLAG_WARP_FROM_COORD,
+                   STIF_MODE_BF16, STIF_MODE_FP32, StifError, check, lib)
 
 _MODES = {"bf16": STIF_MODE_BF16, "fp32": STIF_MODE_FP32}
 
@@ -149,7 +150,7 @@ class STIFQueryDecoder(torch.nn.Module):
     def decode_stacked(self, latent, frames, times, scale=None, mode: str | None = None,
                        rows: tuple[int, int] | None = None, halo: int = 0,
                        out: torch.Tensor | None = None, local_ensemble: bool = False, uint8: bool = False,
-                       test_variant: bool = False) -> torch.Tensor:
+                       test_variant: bool = False, warp_from_coord: bool = False) -> torch.Tensor:
         """Decode to one ``[T,B,3,HH,WW]`` fp32 tensor.  ``rows=(r0,r1)`` restricts the call to a row band
         (``stif_decode_rows``), used by the sharding launcher.  ``uint8=True`` returns what the reference's caller
         saves (``custom_video_test.py:102``): ``(clamp(0,1) * 255).astype(uint8)`` as ``[T,B,HH,WW,3]``."""
@@ -159,7 +160,7 @@ class STIFQueryDecoder(torch.nn.Module):
         tm = _times_matrix(times, B)
         T = tm.shape[0]
         m = (_MODES[mode or self.mode] | (STIF_FLAG_LOCAL_ENSEMBLE if local_ensemble else 0) | (STIF_FLAG_OUT_U8 if uint8 else 0)
-             | (STIF_FLAG_TEST_VARIANT if test_variant else 0))
+             | (STIF_FLAG_TEST_VARIANT if test_variant else 0) | (STIF_FLAG_WARP_FROM_COORD if warp_from_coord else 0))
         ws = self._workspace_for(B, H, W, HH, WW, T, m)
         shape, dtype = ((T, B, HH, WW, 3), torch.uint8) if uint8 else ((T, B, 3, HH, WW), torch.float32)
         if out is None:
@@ -189,6 +190,39 @@ class STIFQueryDecoder(torch.nn.Module):
         if scale is not None and not isinstance(scale, (tuple, list)):
             scale = (int(latent.shape[-2]) * int(scale), int(latent.shape[-1]) * int(scale))
         return list(self.decode_stacked(latent, frames, times, scale, mode="fp32", test_variant=True).unbind(0))
+
+    @staticmethod
+    def memory_window(H: int, W: int, HH: int, WW: int, center) -> tuple[int, int, int, int]:
+        """Rows ``[x0,x1)`` and columns ``[y0,y1)`` of ``decoding_memory``'s 4H x 4W window around ``center`` (normalised
+        (y, x) in [-1,1]), clamped into the raster exactly as the method does (``Sakuya_arch_test.py:636-650``)."""
+        H0, W0 = 4 * H, 4 * W
+        c0 = ((float(center[0]) + 1) / 2) * HH
+        c1 = ((float(center[1]) + 1) / 2) * WW
+        x0, x1, y0, y1 = int(c0) - H0 // 2, int(c0) + H0 - H0 // 2, int(c1) - W0 // 2, int(c1) + W0 - W0 // 2
+        if x0 < 0:
+            x0, x1 = 0, x1 - x0
+        elif x1 > HH:
+            x0, x1 = x0 - (x1 - HH), HH
+        if y0 < 0:
+            y0, y1 = 0, y1 - y0
+        elif y1 > WW:
+            y0, y1 = y0 - (y1 - WW), WW
+        return x0, x1, y0, y1
+
+    def decode_memory(self, latent, frames, times, scale, center) -> list[torch.Tensor]:
+        """``LunaTokis.decoding_memory`` (``Sakuya_arch_test.py:600-861``) WITHOUT its side effects (the hard-coded
+        ``/home/users/...`` directories and JPEG saves, ``:609-651``): stage A on the whole ``scale = (HH, WW)`` raster,
+        stages B-E -- ``decoding_test``'s upsampled frames, ``warpgrid2`` -- on the 4H x 4W window around ``center``.
+        Returns ``T`` tensors ``[B,3,4H,4W]``.  fp32 kernels; the window's rows are decoded as a row band over the full
+        width and the columns are cropped afterwards."""
+        H, W = int(latent.shape[-2]), int(latent.shape[-1])
+        HH, WW = int(scale[0]), int(scale[1])
+        if HH < 4 * H or WW < 4 * W:
+            raise ValueError("decoding_memory needs an output raster at least as large as its 4H x 4W window")
+        x0, x1, y0, y1 = self.memory_window(H, W, HH, WW, center)
+        full = self.decode_stacked(latent, frames, times, (HH, WW), mode="fp32", rows=(x0, x1), halo=HH, test_variant=True,
+                                   warp_from_coord=True)
+        return list(full[:, :, :, x0:x1, y0:y1].contiguous().unbind(0))
 
     def decode_localensemble(self, latent, frames, times, scale=None, mode: str | None = None) -> torch.Tensor:
         """``LunaTokis.decoding_localensemble`` (``Sakuya_arch_test.py:962-1085``): four shifted passes blended by
@@ -330,6 +364,8 @@ def patch_reference_model(model, mode: str = "bf16"):
     model.decoding_fasttest = decoding_fasttest
     model.decoding_localensemble = lambda times=None, scale=None: dec.decode_localensemble(model.feat, model.inp, times, scale)
     model.decoding_test = lambda times=None, scale=None: dec.decode_test(model.feat, model.inp, times, scale)
+    model.decoding_memory = lambda times=None, scale=None, center=None, input_img=None, index=0, save=0: dec.decode_memory(
+        model.feat, model.inp, times, scale, center)   # (input_img / index / save only drive the reference's JPEG side effects)
     model.decoding_fasttest_memory = decoding_fasttest
     model.stif_decoder = dec
     model.stif_refresh_weights = lambda: dec.load_weights(_decoder_state(model))

@@ -12,7 +12,7 @@ from conftest import GOLD
 from oracle import emulate_hoisted as E
 from oracle import port_torch, synth
 from oracle import restate_np as R
-from oracle.make_goldens import CASES, TEST_VARIANT_CASES, checksum
+from oracle.make_goldens import CASES, MEMORY_VARIANT_CASES, TEST_VARIANT_CASES, checksum, window_of
 
 FP32_TOL = 5e-6
 
@@ -155,3 +155,19 @@ def test_decoding_test_variant_restatement(name):
     assert np.abs(st["flow"] - g["flow"][-1]).max() <= 5e-5          # flows reach +-26 px here
     size = None if cfg["scale"] is None else (cfg["H"] * cfg["scale"], cfg["W"] * cfg["scale"])
     assert np.abs(R.decode(lat, fr, w, cfg["times"], size) - g["rgb"]).max() > 1e-3   # not the same function as `decoding`
+
+
+@pytest.mark.parametrize("name", list(MEMORY_VARIANT_CASES))
+def test_decoding_memory_variant_restatement(name):
+    """`decoding_memory` (Sakuya_arch_test.py:600-861; fixtures generated with its file-system side effects neutralised):
+    stage A on the full raster, `decoding_test`'s stages B-E with `warpgrid2` on the clamped 4H x 4W window."""
+    cfg = MEMORY_VARIANT_CASES[name]
+    g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+    w = synth.make_weights(cfg["wseed"], cfg["stress"])
+    lat, fr = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    win = window_of(cfg["H"], cfg["W"], cfg["scale"][0], cfg["scale"][1], cfg["center"])
+    assert tuple(g["window"]) == win
+    out = R.decode(lat, fr, w, cfg["times"], cfg["scale"], upsampled_frames=True, window=win)
+    assert out.shape == g["rgb"].shape and np.abs(out - g["rgb"]).max() <= FP32_TOL
+    crop = R.decode(lat, fr, w, cfg["times"], cfg["scale"], upsampled_frames=True)[:, :, :, win[0]:win[1], win[2]:win[3]]
+    assert np.abs(crop - g["rgb"]).max() > 1e-3          # warpgrid2 makes it more than a crop of decoding_test

@@ -12,7 +12,7 @@ import torch
 from conftest import GOLD
 from oracle import port_torch, synth
 from oracle import restate_np as R
-from oracle.make_goldens import CASES, TEST_VARIANT_CASES
+from oracle.make_goldens import CASES, MEMORY_VARIANT_CASES, TEST_VARIANT_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -440,3 +440,20 @@ def test_random_shapes_fuzz_modes(stif):
         misses += bf.host_pipeline() - before
         assert np.array_equal(host, ref), (H, W, HH, WW, T)
     print(f"fuzz modes: worst ensemble bf16-vs-fp32 {worst:.3e}; host pipeline speculation misses repaired: {misses}")
+
+
+@pytest.mark.parametrize("name", list(MEMORY_VARIANT_CASES))
+def test_decoding_memory_variant(name, decoders, stif):
+    """`LunaTokis.decoding_memory` (windowed zoom queries, Sakuya_arch_test.py:600-861) = STIF_FLAG_TEST_VARIANT |
+    STIF_FLAG_WARP_FROM_COORD on a row band + column crop; fp32 kernels against the reference's own run."""
+    cfg = MEMORY_VARIANT_CASES[name]
+    g = np.load(os.path.join(GOLD, f"case_{name}.npz"))
+    lat, fr = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    dec = decoders(cfg["wseed"], cfg["stress"], "fp32")
+    assert dec.memory_window(cfg["H"], cfg["W"], cfg["scale"][0], cfg["scale"][1], cfg["center"]) == tuple(int(v) for v in g["window"])
+    out = torch.stack(dec.decode_memory(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), cfg["times"], cfg["scale"],
+                                        cfg["center"]), 0)
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - g["rgb"]).max()
+    print(f"{name}: decoding_memory window {tuple(g['window'])} rgb max-abs {err:.3e}")
+    assert out.shape == g["rgb"].shape and err <= 1e-4
