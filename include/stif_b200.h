@@ -53,7 +53,7 @@ extern "C" {
 #define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085), either precision mode */
 #define STIF_FLAG_TEST_VARIANT   0x400  /* decoding_test semantics (Sakuya_arch_test.py:461-598, what VideoSRBaseModel.test runs):
                                          * the frame pair is bilinearly upsampled x4 (:513-514) before every bilinear frame
-                                         * gather.  STIF_MODE_FP32 only in this build. */
+                                         * gather.  STIF_MODE_FP32: any size.  STIF_MODE_BF16: the full x4 raster (HH = 4H, WW = 4W) only. */
 #define STIF_FLAG_WARP_FROM_COORD 0x800 /* warpgrid2 semantics (warplayer.py:41-47): the warp starts from the query's own
                                          * pixel-centre coordinate instead of the linspace base grid.  Together with
                                          * STIF_FLAG_TEST_VARIANT and stif_decode_rows this is decoding_memory

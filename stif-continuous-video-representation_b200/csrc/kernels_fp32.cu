@@ -335,7 +335,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 64, 0), false));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
-    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr, ws.utab);
+    stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr, reinterpret_cast<const float*>(ws.utab));
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
@@ -347,7 +347,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     long n = std::min(chunk, row_end * WW - q0);
     unsigned blocks = (unsigned)((n * 64 + 255) / 256);
     stage_e_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end,
-                                                      ws.flag, ws.act_c, ws.utab);
+                                                      ws.flag, ws.act_c, reinterpret_cast<const float*>(ws.utab));
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 64, 1), false));

@@ -89,6 +89,7 @@ struct K1Params {
   const __half* tab;   // [H*W,256]   TA | TB | TE1 | TE2
   __half* qtab;        // [HH*WW,128] Q1 | Q2
   float* flow;         // [HH*WW,4]
+  const __half* utab;  // decoding_test at x4 only: [HH*WW,192] fp16 UB | UE1 | UE2 (frame terms on the query grid), else null
   float* ftab;         // local-ensemble passes only: F + composed bias, [HH*WW,64] fp32 (stage B reads it at OTHER pixels)
   const uint8_t* wimg;
   long q_begin, q_end;
@@ -356,14 +357,24 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
 }
 
 // acc + bias -> fp16 -> 64 bytes of the projected HR table
-template <class Pf>
-__device__ __forceinline__ void epi_store_qtab(uint32_t (&v)[32], const float* __restrict__ bias, __half* dst, bool valid, Pf&& next_ld) {
+// (ADD: `add` points at 32 fp16 values added to the row -- the upsampled-frame term of decoding_test at x4, which lives on
+// the same grid as the Q table and is sampled with the same taps, so it can ride inside it)
+template <bool ADD = false, class Pf>
+__device__ __forceinline__ void epi_store_qtab(uint32_t (&v)[32], const float* __restrict__ bias, __half* dst, bool valid, Pf&& next_ld,
+                                               const __half* add = nullptr) {
   uint32_t o[16];
+  U8x32 u0, u1;
+  if constexpr (ADD) { u0 = ldg256(add); u1 = ldg256(add + 16); }
 #pragma unroll
   for (int j4 = 0; j4 < 8; ++j4) {
     const float4 b4 = ldc4(bias + 4 * j4);
-    const float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
-    const float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
+    float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
+    float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
+    if constexpr (ADD) {
+      const uint32_t h0 = j4 < 4 ? u0.r[2 * j4] : u1.r[2 * j4 - 8], h1 = j4 < 4 ? u0.r[2 * j4 + 1] : u1.r[2 * j4 - 7];
+      a0.x = add_f16((uint16_t)(h0 & 0xFFFF), a0.x); a0.y = add_f16((uint16_t)(h0 >> 16), a0.y);
+      a1.x = add_f16((uint16_t)(h1 & 0xFFFF), a1.x); a1.y = add_f16((uint16_t)(h1 >> 16), a1.y);
+    }
     o[2 * j4] = pack_half2(a0.x, a0.y);
     o[2 * j4 + 1] = pack_half2(a1.x, a1.y);
   }
@@ -577,7 +588,10 @@ __global__ void __launch_bounds__(512, 1) k0_project_kernel(const __grid_constan
 // =================================================================================================
 // CH = this thread's column half (compile-time so that every bias / weight index is an immediate
 // constant-bank operand instead of a per-thread LDC)
-template <bool ISSUER>
+// UPF = decoding_test at x4 ("upsampled frames"): the bilinear frame gathers of stage B / stage D read the x4-upsampled
+// pair, whose grid IS the query grid at x4 -- stage B's term is the query's own texel (added to gB) and stage D's terms
+// are folded into the Q planes (bilinear(Q;g) + bilinear(UE;g) = bilinear(Q + UE;g)), so K2 runs unchanged.
+template <bool ISSUER, bool UPF = false>
 __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;   // warp-uniform (broadcast from lane 0): constant-bank indices stay uniform-register loads
   const uint32_t wsm = smem_u32(smem);
@@ -648,6 +662,14 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) gB[16 * j + e] = p.c.cB[ch0 + 16 * j + e] + p.c.f3_b[ch0 + 16 * j + e];
+        if constexpr (UPF) {   // + UB at the query's own texel of the upsampled frames
+          const U8x32 ub = ldg256(p.utab + qc * 192 + ch0 + 16 * j);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            gB[16 * j + 2 * e] = add_f16((uint16_t)(ub.r[e] & 0xFFFF), gB[16 * j + 2 * e]);
+            gB[16 * j + 2 * e + 1] = add_f16((uint16_t)(ub.r[e] >> 16), gB[16 * j + 2 * e + 1]);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const U8x32 v = ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
@@ -662,8 +684,13 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
 
     trace_mark(cx, 4);
     layer_finish<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
-      if (i < 2) epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
-      else epi_flow_first_layer(v, cx.lane_addr + kColAin + CH * 16, gB, pf);
+      if (i < 2) {
+        if constexpr (UPF) epi_store_qtab<true>(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf,
+                                                p.utab + qc * 192 + 64 * (i + 1) + ch0);
+        else epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
+      } else {
+        epi_flow_first_layer(v, cx.lane_addr + kColAin + CH * 16, gB, pf);
+      }
     });
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
@@ -683,6 +710,46 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
           make_float4(mine.x + o.x + p.c.l3_b[0], mine.y + o.y + p.c.l3_b[1], mine.z + o.z + p.c.l3_b[2], mine.w + o.w + p.c.l3_b[3]);
     }
   }
+}
+
+// decoding_test at x4 on the tensor-core path: the fused loop with the upsampled-frame terms (see k1_tile_loop, UPF)
+__global__ void __launch_bounds__(576, 1) k1_stage_ab_upf_kernel(const __grid_constant__ K1Params p) {
+  const CtaSetup s = cta_prologue(k1Bars, 0, p.wimg, k1WBytes, 512);
+  {
+    float* cs = reinterpret_cast<float*>(smem + k1Const);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) cs[kc1L3W + i] = p.c.l3_w[i];
+    __syncthreads();
+  }
+  WgCtx cx = make_wg(s);
+  mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.issuer) k1_tile_loop<true, true>(p, s, cx);
+  else k1_tile_loop<false, true>(p, s, cx);
+  cta_epilogue(s.tmem_base, 512);
+}
+
+// fp16 table of the upsampled-frame terms for that kernel: utab[4H*4W, 192] = w_up . bilinear_upsample_x4(frames)
+// (ATen's formula, as project_frames_up4_kernel in kernels_fp32.cu; fp32 arithmetic, fp16 storage like the other tables)
+__global__ void project_frames_up4_half_kernel(const float* __restrict__ frames, int H, int W, const float* __restrict__ w_up,
+                                               __half* __restrict__ utab) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)16 * H * W * 192) return;
+  const int c = (int)(i % 192);
+  const long texel = i / 192;
+  const int y = (int)(texel / (4 * W)), x = (int)(texel % (4 * W));
+  const float sy = fmaxf(0.f, __fadd_rn(__fmul_rn(0.25f, (float)y + 0.5f), -0.5f)), sx = fmaxf(0.f, __fadd_rn(__fmul_rn(0.25f, (float)x + 0.5f), -0.5f));
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float ly = __fadd_rn(sy, -(float)y0), lx = __fadd_rn(sx, -(float)x0);
+  const float wy0 = __fadd_rn(1.f, -ly), wx0 = __fadd_rn(1.f, -lx);
+  float s = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 6; ++ch) {
+    const float* f = frames + (long)ch * H * W;
+    const float top = __fadd_rn(__fmul_rn(wx0, f[(long)y0 * W + x0]), __fmul_rn(lx, f[(long)y0 * W + x1]));
+    const float bot = __fadd_rn(__fmul_rn(wx0, f[(long)y1 * W + x0]), __fmul_rn(lx, f[(long)y1 * W + x1]));
+    s = fmaf(w_up[c * 6 + ch], __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly, bot)), s);
+  }
+  utab[i] = __float2half_rn(s);
 }
 
 __global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_constant__ K1Params p) {
@@ -1063,6 +1130,8 @@ cudaError_t launch_pdl(void (*kern)(const P), int grid, int block, size_t smem_b
 
 struct TcWeights {
   uint8_t* d_k0 = nullptr;
+  uint8_t* d_k0_lat = nullptr;   // decoding_test variant: W_tab without the frame columns of TB | TE1 | TE2
+  float* d_w_up = nullptr;       // ... which become this [192,6] map on the upsampled frames
   uint8_t* d_k1 = nullptr;
   uint8_t* d_k2 = nullptr;
   K1Consts c1{};
@@ -1072,12 +1141,15 @@ struct TcWeights {
 
 TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   auto* t = new TcWeights();
-  std::vector<uint8_t> i0, i1, i2;
+  std::vector<uint8_t> i0, i0lat, i1, i2;
   {
     std::vector<float> wpad((size_t)256 * 256, 0.f);   // K padded 198 -> 256 with zeros
     for (int r = 0; r < 256; ++r)
       for (int k = 0; k < 198; ++k) wpad[(size_t)r * 256 + k] = hw.w_tab[(size_t)r * 198 + k];
     append_sw128_image(i0, wpad.data(), 256, 256);
+    for (int r = 0; r < 256; ++r)
+      for (int k = 0; k < 198; ++k) wpad[(size_t)r * 256 + k] = hw.w_tab_lat[(size_t)r * 198 + k];
+    append_sw128_image(i0lat, wpad.data(), 256, 256);
   }
   append_sw128_image(i1, hw.f1_w.data(), 64, 64);
   append_sw128_image(i1, hw.f2_w.data(), 256, 64);
@@ -1096,6 +1168,11 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaMalloc(&t->d_k1, i1.size());
   if (e == cudaSuccess) e = cudaMalloc(&t->d_k2, i2.size());
   if (e == cudaSuccess) e = cudaMemcpy(t->d_k0, i0.data(), i0.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_k0_lat, i0lat.size());
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_k0_lat, i0lat.data(), i0lat.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_w_up, hw.w_up.size() * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpy(t->d_w_up, hw.w_up.data(), hw.w_up.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_upf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaMemcpy(t->d_k1, i1.data(), i1.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(t->d_k2, i2.data(), i2.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k0_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0Smem);
@@ -1136,18 +1213,27 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
 void tc_weights_destroy(TcWeights* t) {
   if (!t) return;
   if (t->d_k0) cudaFree(t->d_k0);
+  if (t->d_k0_lat) cudaFree(t->d_k0_lat);
+  if (t->d_w_up) cudaFree(t->d_w_up);
   if (t->d_k1) cudaFree(t->d_k1);
   if (t->d_k2) cudaFree(t->d_k2);
   delete t;
 }
 
+cudaError_t project_frames_up4_tc(const LaunchCtx& cx, const TcWeights* tw, const float* frames6, int H, int W, void* utab) {
+  const long n = (long)16 * H * W * 192;
+  project_frames_up4_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx.stream>>>(frames6, H, W, tw->d_w_up, reinterpret_cast<__half*>(utab));
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
-                              int W, void* tab, int row_begin, int row_end) {
+                              int W, void* tab, int row_begin, int row_end, bool test_variant) {
   K0Params p;
   p.latent = latent192;
   p.frames = frames6;
   p.tab = reinterpret_cast<__half*>(tab);
-  p.wimg = tw->d_k0;
+  p.wimg = test_variant ? tw->d_k0_lat : tw->d_k0;
   p.HW = (long)H * W;
   p.m_begin = (long)row_begin * W;
   p.m_end = (long)row_end * W;
@@ -1199,7 +1285,7 @@ void trace_dump(const char* kernel, cudaStream_t stream) {
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage) {
   const long WW = geo.WW;
-  if (stage == 1 || stage == 3 || stage == 4) {   // 1: fused stage A+B; 3 / 4: stage A / stage B of a local-ensemble pass
+  if (stage == 1 || stage == 3 || stage == 4 || stage == 5) {   // 1: fused stage A+B; 3 / 4: stage A / B of a local-ensemble pass; 5: fused, decoding_test at x4
     K1Params p;
     p.c = tw->c1;
     for (int c = 0; c < 64; ++c) {
@@ -1211,6 +1297,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.qtab = reinterpret_cast<__half*>(ws.qtab);
     p.flow = ws.flow;
     p.ftab = ws.ftab;
+    p.utab = reinterpret_cast<const __half*>(ws.utab);
     p.wimg = tw->d_k1;
     p.q_begin = k1_row_begin * WW;
     p.q_end = k1_row_end * WW;
@@ -1219,10 +1306,12 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     p.trace = trace_buffer();
     p.dephase_clk = dephase_clocks(1);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
-    if (stage != 1 && !ws.ftab) return cudaErrorInvalidValue;
+    if ((stage == 3 || stage == 4) && !ws.ftab) return cudaErrorInvalidValue;
+    if (stage == 5 && !ws.utab) return cudaErrorInvalidValue;
     if (cudaError_t e = stage == 1   ? launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)
                         : stage == 3 ? launch_pdl(k1_ensemble_kernel<1>, grid, 576, k1Smem, cx.stream, p)
-                                     : launch_pdl(k1_ensemble_kernel<2>, grid, 576, k1Smem, cx.stream, p))
+                        : stage == 4 ? launch_pdl(k1_ensemble_kernel<2>, grid, 576, k1Smem, cx.stream, p)
+                                     : launch_pdl(k1_stage_ab_upf_kernel, grid, 576, k1Smem, cx.stream, p))
       return e;
     ++*cx.launch_counter;
     trace_dump("K1", cx.stream);

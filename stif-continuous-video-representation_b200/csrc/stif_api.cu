@@ -116,7 +116,7 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
   ws.flow = (float*)take(Q * 4 * sizeof(float));
   ws.flag = (int*)take(256);
   if (mode & STIF_FLAG_OUT_U8) ws.rgb32 = (float*)take(Q * 3 * sizeof(float));
-  if (mode & STIF_FLAG_TEST_VARIANT) ws.utab = (float*)take((size_t)16 * H * W * 192 * sizeof(float));
+  if (mode & STIF_FLAG_TEST_VARIANT) ws.utab = take((size_t)16 * H * W * 192 * esz);
   if (fp32) {
     ws.chunk = std::min<size_t>(Q, (size_t)1 << 18);
     ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
@@ -440,8 +440,14 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
   const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0, u8 = (mode & STIF_FLAG_OUT_U8) != 0;
   const bool test_variant = (mode & STIF_FLAG_TEST_VARIANT) != 0, warp_from_coord = (mode & STIF_FLAG_WARP_FROM_COORD) != 0;
-  if ((test_variant || warp_from_coord) && (prec != STIF_MODE_FP32 || ensemble))
-    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT / STIF_FLAG_WARP_FROM_COORD are available with STIF_MODE_FP32 (without the ensemble flag) in this build");
+  // tensor-core kernels: decoding_test only at x4, where the upsampled-frame grid IS the query grid (k1_tile_loop, UPF)
+  const bool tc_variant = test_variant && prec == STIF_MODE_BF16;
+  if ((test_variant || warp_from_coord) && ensemble)
+    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT / STIF_FLAG_WARP_FROM_COORD cannot be combined with STIF_FLAG_LOCAL_ENSEMBLE");
+  if (warp_from_coord && prec != STIF_MODE_FP32)
+    return set_error(STIF_EINVAL, "STIF_FLAG_WARP_FROM_COORD is available with STIF_MODE_FP32 only in this build");
+  if (tc_variant && (HH != 4 * H || WW != 4 * W || row_begin != 0 || row_end != HH))
+    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT with STIF_MODE_BF16 needs the full x4 raster (HH = 4H, WW = 4W); use STIF_MODE_FP32 otherwise");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
   if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
@@ -450,7 +456,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (workspace_bytes < need)
     return set_error(STIF_ENOMEM, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
   CUDA_OR_RETURN(cudaSetDevice(d->device));
-  if (hp && prec == STIF_MODE_BF16 && !ensemble) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
+  if (hp && prec == STIF_MODE_BF16 && !ensemble && !test_variant) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
   const Geometry* geo = nullptr;
   if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo, warp_from_coord)) return rc;
   Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
@@ -478,10 +484,13 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
         CUDA_OR_RETURN(cudaStreamWaitEvent(stream, ev, 0));
       }
       ScopedSpan sp(d, stream, 0);
-      if (prec == STIF_MODE_BF16) CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
+      if (prec == STIF_MODE_BF16) {
+        CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1, tc_variant));
+        if (tc_variant && k == nbands - 1) CUDA_OR_RETURN(project_frames_up4_tc(cx, d->tcw, fr_b, H, W, ws.utab));
+      }
       else if (k == nbands - 1) {
         CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false, test_variant));
-        if (test_variant) CUDA_OR_RETURN(project_frames_up4(cx, d->w32, fr_b, H, W, ws.utab));
+        if (test_variant) CUDA_OR_RETURN(project_frames_up4(cx, d->w32, fr_b, H, W, (float*)ws.utab));
       }
     }
     for (int c = 0; c < T; ++c) {
@@ -501,7 +510,8 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
         ScopedSpan sp(d, stream, stage);
         cudaError_t e = (prec == STIF_MODE_FP32)
                             ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
-                            : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage);
+                            : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab,
+                                             stage == 1 && tc_variant ? 5 : stage);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
       if (u8) CUDA_OR_RETURN(rgb_to_u8_hwc(cx, ws.rgb32, out_u8, HH, WW, row_begin, row_end));

@@ -75,7 +75,8 @@ struct Workspace {
   float* ftab;    // local-ensemble mode: F = 30 Wl0[:, :64] HRfeat for the whole slab [HH*WW,64]
   float* pred;    // local-ensemble mode: one pass's prediction [3,HH*WW]
   int* flag;      // device int: row-band halo violation flag
-  float* utab;    // STIF_FLAG_TEST_VARIANT: [4H*4W,192] fp32 UB | UE1 | UE2 = frame columns applied to the x4-upsampled frames
+  void* utab;     // STIF_FLAG_TEST_VARIANT: [4H*4W,192] UB | UE1 | UE2 = frame columns applied to the x4-upsampled frames
+                  // (fp32 in FP32 mode, fp16 in BF16 mode)
   float* rgb32;   // STIF_FLAG_OUT_U8: fp32 staging of one slab [3,HH*WW] ahead of the uint8 conversion
   size_t chunk;   // queries per activation chunk (FP32 mode)
   size_t total_bytes;
@@ -118,8 +119,9 @@ HostBandPlan plan_host_bands(int H, int W, int HH, int WW, int G, int bands_hint
 
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage);
+cudaError_t project_frames_up4_tc(const LaunchCtx& cx, const TcWeights* tw, const float* frames6, int H, int W, void* utab);
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
-                              int W, void* tab /* fp16 [H*W,256] */, int row_begin, int row_end);
+                              int W, void* tab /* fp16 [H*W,256] */, int row_begin, int row_end, bool test_variant = false);
 int tc_selftest(int device, std::string& report);
 
 }  // namespace stif

@@ -183,13 +183,18 @@ class STIFQueryDecoder(torch.nn.Module):
         """``LunaTokis.decoding`` return convention: list of ``T`` tensors ``[B,3,HH,WW]``."""
         return list(self.decode_stacked(latent, frames, times, scale, mode).unbind(0))
 
-    def decode_test(self, latent, frames, times, scale=None) -> list[torch.Tensor]:
+    def decode_test(self, latent, frames, times, scale=None, mode: str | None = None) -> list[torch.Tensor]:
         """``LunaTokis.decoding_test`` (``Sakuya_arch_test.py:461-598``, what ``VideoSRBaseModel.test`` runs): as ``decode`` but
         the bilinear frame gathers read the x4-upsampled frame pair.  ``scale`` is the reference's integer factor
-        (``:467``) or, as the shipped evaluation loops pass it, an output size tuple.  fp32 kernels in this build."""
+        (``:467``) or, as the shipped evaluation loops pass it, an output size tuple.  At x4 (the default) the decoder's own
+        mode is used -- on the tensor-core path the upsampled-frame terms share the query grid and ride inside the Q
+        table; any other size runs on the fp32 kernels."""
+        H, W = int(latent.shape[-2]), int(latent.shape[-1])
         if scale is not None and not isinstance(scale, (tuple, list)):
-            scale = (int(latent.shape[-2]) * int(scale), int(latent.shape[-1]) * int(scale))
-        return list(self.decode_stacked(latent, frames, times, scale, mode="fp32", test_variant=True).unbind(0))
+            scale = (H * int(scale), W * int(scale))
+        x4 = scale is None or (int(scale[0]), int(scale[1])) == (4 * H, 4 * W)
+        return list(self.decode_stacked(latent, frames, times, scale, mode=(mode or self.mode) if x4 else "fp32",
+                                        test_variant=True).unbind(0))
 
     @staticmethod
     def memory_window(H: int, W: int, HH: int, WW: int, center) -> tuple[int, int, int, int]:

@@ -457,3 +457,29 @@ def test_decoding_memory_variant(name, decoders, stif):
     err = np.abs(out.cpu().numpy() - g["rgb"]).max()
     print(f"{name}: decoding_memory window {tuple(g['window'])} rgb max-abs {err:.3e}")
     assert out.shape == g["rgb"].shape and err <= 1e-4
+
+
+def test_decoding_test_variant_tensor_core_x4(decoders):
+    """decoding_test at x4 on the tensor-core kernels: the upsampled-frame grid is the query grid there, so stage B's term is
+    the query's own texel and stage D's terms are folded into the Q planes.  Against the reference fixture (bf16
+    tolerance) and, at 270x480 -> 1080x1920, against the fp32 kernels; any other size falls back to fp32."""
+    cfg = TEST_VARIANT_CASES["testvar_x4_init"]
+    g = np.load(os.path.join(GOLD, "case_testvar_x4_init.npz"))
+    lat, fr = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    bf = decoders(cfg["wseed"], cfg["stress"], "bf16")
+    out = torch.stack(bf.decode_test(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), cfg["times"], None), 0)
+    torch.cuda.synchronize()
+    err = np.abs(out.cpu().numpy() - g["rgb"]).max()
+    lat, fr = synth.smooth_inputs(14, 1, 270, 480, 0.05)
+    L, F = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    bfs, fps = decoders(0, True, "bf16"), decoders(0, True, "fp32")
+    a = torch.stack(bfs.decode_test(L, F, [0.0, 0.5], 4), 0)
+    b = torch.stack(fps.decode_test(L, F, [0.0, 0.5], 4), 0)
+    plain = torch.stack(bfs.decode(L, F, [0.0, 0.5], None), 0)
+    err2 = float((a - b).abs().max())
+    print(f"decoding_test x4 tensor-core: vs reference fixture {err:.3e}; 1080p vs fp32 kernels {err2:.3e} "
+          f"(differs from plain decoding by {float((a - plain).abs().max()):.2e})")
+    assert err <= 2e-2 and err2 <= 2e-2 and float((a - plain).abs().max()) > 1e-3
+    c = torch.stack(bfs.decode_test(L[:, :, :, :12, :10].contiguous(), F[:, :, :, :12, :10].contiguous(), [0.3], 3), 0)   # x3 -> fp32 path
+    d = torch.stack(fps.decode_test(L[:, :, :, :12, :10].contiguous(), F[:, :, :, :12, :10].contiguous(), [0.3], 3), 0)
+    assert torch.equal(c, d)
