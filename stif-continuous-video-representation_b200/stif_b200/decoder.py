@@ -395,6 +395,19 @@ def install_class_patch(luna_tokis_cls, mode: str = "bf16"):
     def decoding_fasttest(self, times=None, scale=None):
         return _dec(self).decode_stacked(self.feat, self.inp, list(times), scale)[:, 0]
 
+    def decoding_localensemble(self, times=None, scale=None):
+        return _dec(self).decode_localensemble(self.feat, self.inp, times, scale)
+
+    def decoding_test(self, times=None, scale=None):
+        return _dec(self).decode_test(self.feat, self.inp, times, scale)
+
+    def decoding_memory(self, times=None, scale=None, center=None, input_img=None, index=0, save=0):
+        return _dec(self).decode_memory(self.feat, self.inp, times, scale, center)   # (no JPEG side effects)
+
     luna_tokis_cls.decoding = decoding
     luna_tokis_cls.decoding_fasttest = decoding_fasttest
+    luna_tokis_cls.decoding_fasttest_memory = decoding_fasttest
+    luna_tokis_cls.decoding_localensemble = decoding_localensemble
+    luna_tokis_cls.decoding_test = decoding_test
+    luna_tokis_cls.decoding_memory = decoding_memory
     return luna_tokis_cls

@@ -483,3 +483,58 @@ def test_decoding_test_variant_tensor_core_x4(decoders):
     c = torch.stack(bfs.decode_test(L[:, :, :, :12, :10].contiguous(), F[:, :, :, :12, :10].contiguous(), [0.3], 3), 0)   # x3 -> fp32 path
     d = torch.stack(fps.decode_test(L[:, :, :, :12, :10].contiguous(), F[:, :, :, :12, :10].contiguous(), [0.3], 3), 0)
     assert torch.equal(c, d)
+
+
+class _SineLayer(torch.nn.Module):          # SIREN.py:14-45 shape: a Linear called `linear`
+    def __init__(self, i, o):
+        super().__init__()
+        self.linear = torch.nn.Linear(i, o)
+
+
+class _Siren(torch.nn.Module):              # SIREN.py:48-79 shape: `net` = sine layers + a final plain Linear
+    def __init__(self, dims):
+        super().__init__()
+        self.net = torch.nn.Sequential(*[_SineLayer(dims[i], dims[i + 1]) for i in range(len(dims) - 2)],
+                                       torch.nn.Linear(dims[-2], dims[-1]))
+
+
+class _StandInLuna(torch.nn.Module):
+    """The attributes of LunaTokis the patch touches (Sakuya_arch_test.py:306-311, :361, :1224): three SIREN sub-modules with
+    the reference's state-dict key layout, `feat`, `inp`.  (The reference itself cannot travel to the GPU box.)"""
+    def __init__(self, weights):
+        super().__init__()
+        from stif_b200.decoder import NET_SHAPES
+        for net, dims in NET_SHAPES.items():
+            setattr(self, net, _Siren(dims))
+        self.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
+
+
+@pytest.mark.parametrize("how", ["instance", "class"])
+def test_drop_in_patch_rebinds_every_decode_method(how, stif):
+    """patch_reference_model / install_class_patch: weights snapshotted from the three sub-modules' state dicts, and
+    decoding / decoding_fasttest / decoding_localensemble / decoding_test / decoding_memory answer with the reference's
+    calling conventions and return types; checked against the reference fixtures of the same seeded case."""
+    from stif_b200.decoder import install_class_patch, patch_reference_model
+    cfg = CASES["x4_init"]
+    g = np.load(os.path.join(GOLD, "case_x4_init.npz"))
+    gt = np.load(os.path.join(GOLD, "case_testvar_x4_init.npz"))
+    lat, fr = synth.make_inputs(cfg["iseed"], 1, cfg["H"], cfg["W"], cfg["latent_std"])
+    if how == "class":
+        cls = type("PatchedLuna", (_StandInLuna,), {})
+        install_class_patch(cls, mode="fp32")
+        model = cls(synth.make_weights(cfg["wseed"], cfg["stress"])).cuda()
+    else:
+        model = patch_reference_model(_StandInLuna(synth.make_weights(cfg["wseed"], cfg["stress"])).cuda(), mode="fp32")
+    model.feat, model.inp = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    times = [torch.tensor([[float(t)]]).cuda() for t in cfg["times"]]           # custom_video_test.py:50
+    preds = model.decoding(times, cfg["scale"])
+    assert isinstance(preds, list) and len(preds) == len(times) and preds[0].shape == (1, 3, 64, 64)
+    assert np.abs(torch.stack(preds, 0).cpu().numpy() - g["rgb"]).max() <= 1e-4
+    fast = model.decoding_fasttest([float(t) for t in cfg["times"]], cfg["scale"])
+    assert fast.shape == (2, 3, 64, 64) and np.abs(fast.cpu().numpy() - g["rgb_fasttest"]).max() <= 1e-4
+    ens = model.decoding_localensemble([float(t) for t in cfg["times"]], cfg["scale"])
+    assert np.abs(ens.cpu().numpy() - g["rgb_localensemble"]).max() <= 1e-4
+    tst = model.decoding_test(times, None)
+    assert np.abs(torch.stack(tst, 0).cpu().numpy() - gt["rgb"]).max() <= 1e-4
+    win = model.decoding_memory(times, (100, 90), np.array([0.1, -0.2]), input_img=None)
+    assert isinstance(win, list) and win[0].shape == (1, 3, 64, 64)
