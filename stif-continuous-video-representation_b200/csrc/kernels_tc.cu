@@ -286,8 +286,8 @@ __device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_base, uint32_t w
   layer_finish<NC, KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of, epi);
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// (No software prefetch: an L2 prefetch of the next tile's Q lines paid off while both workgroups gathered at once; with the
+// gather turns it costs 2 % of K2, and exact per-tap prefetches cost 3 %.)
 
 // which of a thread's 16 sine pairs go to the FMA-pipe polynomial (evenly interleaved with the MUFU ones)
 __host__ __device__ constexpr bool use_poly(int j) { return ((j * kPolyPairs) % 16) < kPolyPairs; }
@@ -1039,19 +1039,6 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
     trace_mark(cx, 1);
-    if constexpr (!ISSUER) {  // L2 prefetch for this WG's NEXT tile: the lines a small flow would touch (own pixel, rows -1/0/+1).
-       // Pure hint: a wrong guess costs nothing but the prefetch itself.
-      bool vn;
-      const long qn = k2_query(p, tile + (long)gridDim.x * 2, cx.row, vn);
-      if (vn && tile + (long)gridDim.x * 2 < ntiles) {
-        const char* base = reinterpret_cast<const char*>(p.qtab) + CH * 128;
-        const long W2 = (long)p.g.WW;
-        prefetch_l2(base + qn * 256);
-        if (qn >= W2) prefetch_l2(base + (qn - W2) * 256);
-        if (qn + W2 < p.plane) prefetch_l2(base + (qn + W2) * 256);
-        if (CH == 0) prefetch_l2(reinterpret_cast<const float4*>(p.flow) + qn);
-      }
-    }
     if constexpr (!ISSUER) {
       k2_gather_blend(p, a0, stg, warp_in_wg, lane);
       fence_proxy_async_smem();
