@@ -920,6 +920,7 @@ __device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bo
 __device__ __forceinline__ int tap_slot(int qi) { return (qi >> 2) * 32 + (qi & 3) * 6; }
 
 // phase 1 (bilinear footprints -> per-warp staging); issued one tile ahead, under the 256->256 layer's first MMA wait
+template <bool BAND>
 __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile, int warp_in_wg, int lane) {
   const Geometry& g = p.g;
   {
@@ -935,12 +936,14 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
     // Row-band launches: rows outside [band_lo, band_hi) of the Q table (and the LR rows behind them) may not be
     // written yet.  A tap that carries weight there is a halo violation (flagged; the host repeats the launch);
     // a zero-weight tap is redirected to data that certainly exists (the query's own pixel / texel 0), because
-    // 0 x stale bits is not 0 when the bits are a NaN.  (Full-raster launches: the window is everything.)
+    // 0 x stale bits is not 0 when the bits are a NaN.  (BAND = false: full-raster launches, where every table row exists and the check is compiled out.)
+    if constexpr (BAND) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (hr.w[k] == 0.f) hr.off[k] = (int)q;
-      else if (hr.off[k] < p.band_lo_off || hr.off[k] >= p.band_hi_off) atomicOr(p.flag, 1);
-      if (lr.w[k] == 0.f) lr.off[k] = 0;
+      for (int k = 0; k < 4; ++k) {
+        if (hr.w[k] == 0.f) hr.off[k] = (int)q;
+        else if (hr.off[k] < p.band_lo_off || hr.off[k] >= p.band_hi_off) atomicOr(p.flag, 1);
+        if (lr.w[k] == 0.f) lr.off[k] = 0;
+      }
     }
     const uint32_t cb = which * 128u;
     uint4* dst = stg + tap_slot(qi);
@@ -1017,7 +1020,7 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
   __syncwarp();
 }
 
-template <bool ISSUER>
+template <bool ISSUER, bool BAND>
 __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
@@ -1030,7 +1033,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   const int ch0 = CH * 32;
 
   const long tile_first = (long)blockIdx.x * 2 + cx.wg;
-  if (tile_first < ntiles && !ISSUER) k2_gather_taps(p, stg, tile_first, warp_in_wg, lane);
+  if (tile_first < ntiles && !ISSUER) k2_gather_taps<BAND>(p, stg, tile_first, warp_in_wg, lane);
   for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
     bool valid;
@@ -1059,7 +1062,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     layer_begin<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
     {  // footprints of this WG's next tile, computed while the first 256->256 chunk is on the tensor pipe
       const long tile_next = tile + (long)gridDim.x * 2;
-      if (tile_next < ntiles && !ISSUER) k2_gather_taps(p, stg, tile_next, warp_in_wg, lane);
+      if (tile_next < ntiles && !ISSUER) k2_gather_taps<BAND>(p, stg, tile_next, warp_in_wg, lane);
     }
     layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf); });
@@ -1078,6 +1081,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   }
 }
 
+template <bool BAND>
 __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
   {
@@ -1088,8 +1092,8 @@ __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_const
   WgCtx cx = make_wg(s);
   if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
-  if (cx.issuer) k2_tile_loop<true>(p, s, cx);
-  else k2_tile_loop<false>(p, s, cx);
+  if (cx.issuer) k2_tile_loop<true, BAND>(p, s, cx);
+  else k2_tile_loop<false, BAND>(p, s, cx);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -1164,14 +1168,15 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaMemcpy(t->d_k2, i2.data(), i2.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k0_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k0Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (getenv("STIF_DEBUG_ATTRS")) {
     cudaFuncAttributes a;
     cudaFuncGetAttributes(&a, k1_stage_ab_kernel);
     fprintf(stderr, "k1: regs %d maxThreads %d smem static %zu local %zu\n", a.numRegs, a.maxThreadsPerBlock, a.sharedSizeBytes, a.localSizeBytes);
-    cudaFuncGetAttributes(&a, k2_stage_cde_kernel);
+    cudaFuncGetAttributes(&a, k2_stage_cde_kernel<false>);
     fprintf(stderr, "k2: regs %d maxThreads %d smem static %zu local %zu\n", a.numRegs, a.maxThreadsPerBlock, a.sharedSizeBytes, a.localSizeBytes);
   }
   if (e != cudaSuccess) {
@@ -1325,7 +1330,10 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.trace = trace_buffer();
   p.dephase_clk = dephase_clocks(2);
   if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
-  if (cudaError_t e = launch_pdl(k2_stage_cde_kernel, grid, 576, k2Smem, cx.stream, p)) return e;
+  const bool band = k1_row_begin > 0 || k1_row_end < geo.HH;   // stage A+B rows are incomplete: check every weighted tap
+  if (cudaError_t e = band ? launch_pdl(k2_stage_cde_kernel<true>, grid, 576, k2Smem, cx.stream, p)
+                           : launch_pdl(k2_stage_cde_kernel<false>, grid, 576, k2Smem, cx.stream, p))
+    return e;
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
   return cudaGetLastError();
