@@ -11,7 +11,8 @@ stalls = collections.Counter()
 tot_ex = tot_s = 0
 top = []
 for r in rows[2:]:
-    if len(r) <= iex: continue
+    if r and r[0] == "Kernel Name": break      # a second kernel matched the regex: summarise the first section only
+    if len(r) <= iex or r[ia] == "Address": continue
     op = r[isrc].split()
     if not op: continue
     name = op[1] if op[0].startswith("@") and len(op) > 1 else op[0]
