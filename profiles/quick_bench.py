@@ -11,5 +11,5 @@ for _ in range(3): dec.decode_stacked(lat, fr, [0.0, 0.5], (1080, 1920), out=out
 torch.cuda.synchronize(); dec.profile(True); dec.profile_read()
 for _ in range(10): dec.decode_stacked(lat, fr, [0.0, 0.5], (1080, 1920), out=out)
 p = dec.profile_read()
-print(os.environ.get("STIF_DEPHASE_K1"), os.environ.get("STIF_DEPHASE_K2"), "ms/launch K0,K1,K2:", [round(m / max(c, 1), 4) for m, c in zip(p["ms"], p["count"])],
+print("ms/launch K0,K1,K2:", [round(m / max(c, 1), 4) for m, c in zip(p["ms"], p["count"])],
       "step ms", round(sum(p["ms"]) / 10, 4), "checksum", float(out.double().abs().mean()))

@@ -375,8 +375,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
   const long Q = (long)g0.HH * g0.WW;
   const float* tab = reinterpret_cast<const float*>(ws.tab);
   float* qtab = reinterpret_cast<float*>(ws.qtab);
-  const Vec64 cA = time_constant(hw.a_t, hw.a_b, t), cB = time_constant(hw.b_t, hw.b_b, t),
-              cE = time_constant(hw.e_t, hw.e_b, t);
+  const Vec64 cA = time_constant(hw.a_t, hw.a_b, t), cB = time_constant(hw.b_t, hw.b_b, t);   // (stage E's constant: decode_slab_fp32)
   const long chunk = (long)ws.chunk;
   for (int k = 0; k < 4; ++k) {
     const Geometry& geo = geo_pass[k];
@@ -410,7 +409,6 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
   }
-  (void)cA;
   return cudaSuccess;
 }
 

@@ -42,7 +42,6 @@ constexpr int kTile = 128;
 #define KPOLY 0
 #endif
 constexpr int kPolyPairs = KPOLY;   // of the 16 sine pairs per thread per chunk, this many run on the FMA pipe (poly_sin2)
-constexpr int kDephaseK1 = 0, kDephaseK2 = 0;   // default WG1 start offsets (clocks); see dephase_clocks()
 constexpr uint32_t kColA = 0;     // A-area: 256-wide activations, channel k at column k/2
 constexpr uint32_t kColAin = 96;  // 64-wide activations live in the last 32 columns of the A-area
 constexpr uint32_t kColD = 128;   // two accumulator slots: [128,192), [192,256)
@@ -94,7 +93,6 @@ struct K1Params {
   const uint8_t* wimg;
   long q_begin, q_end;
   long long* trace;    // debug: clock64 timestamps of block 0 (STIF_TRACE=<file>), else null
-  int dephase_clk;     // WG1 starts this many clocks after WG0 so the two tiles' phases interleave
 };
 struct K2Params {
   K2Consts c;
@@ -112,7 +110,6 @@ struct K2Params {
   int band_lo_off, band_hi_off;   // Q-table pixels [lo, hi) exist (stage A+B rows of this launch); taps outside raise *flag
   int* flag;
   long long* trace;
-  int dephase_clk;
 };
 struct K0Params {
   const float* latent;  // [192, HW]
@@ -292,7 +289,6 @@ __device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_base, uint32_t w
 // which of a thread's 16 sine pairs go to the FMA-pipe polynomial (evenly interleaved with the MUFU ones)
 __host__ __device__ constexpr bool use_poly(int j) { return ((j * kPolyPairs) % 16) < kPolyPairs; }
 
-__device__ __forceinline__ float2 ldc2(const float* p) { return *reinterpret_cast<const float2*>(p); }
 // 4 consecutive constants in one 128-bit constant-bank load (all bias / weight arrays are 16-byte aligned at 4-element steps)
 __device__ __forceinline__ float4 ldc4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -1024,7 +1020,7 @@ template <bool ISSUER, bool BAND>
 __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
-  const int lane = threadIdx.x & 31, warp = cx.slot & 15, warp_in_wg = cx.warp_in_wg;
+  const int lane = threadIdx.x & 31, warp_in_wg = cx.warp_in_wg;
   uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
   uint4* stg = reinterpret_cast<uint4*>(a0 + warp_in_wg * 2048);
   float4* part = reinterpret_cast<float4*>(smem + k2Part) + cx.wg * 128;
@@ -1248,15 +1244,6 @@ long long* trace_buffer() {
   }
   return buf;
 }
-// tuning knob (STIF_DEPHASE_K1 / STIF_DEPHASE_K2, clocks)
-int dephase_clocks(int kernel) {
-  static int v[3] = {-1, -1, -1};
-  if (v[kernel] < 0) {
-    const char* e = getenv(kernel == 1 ? "STIF_DEPHASE_K1" : "STIF_DEPHASE_K2");
-    v[kernel] = e ? atoi(e) : (kernel == 1 ? kDephaseK1 : kDephaseK2);
-  }
-  return v[kernel];
-}
 void trace_dump(const char* kernel, cudaStream_t stream) {
   long long* buf = trace_buffer();
   if (!buf) return;
@@ -1296,7 +1283,6 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
     const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
     p.trace = trace_buffer();
-    p.dephase_clk = dephase_clocks(1);
     if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
     if ((stage == 3 || stage == 4) && !ws.ftab) return cudaErrorInvalidValue;
     if (stage == 5 && !ws.utab) return cudaErrorInvalidValue;
@@ -1328,7 +1314,6 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   const long ntiles = (long)p.tiles_x * ((row_end - row_begin + 7) / 8);
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
   p.trace = trace_buffer();
-  p.dephase_clk = dephase_clocks(2);
   if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
   const bool band = k1_row_begin > 0 || k1_row_end < geo.HH;   // stage A+B rows are incomplete: check every weighted tap
   if (cudaError_t e = band ? launch_pdl(k2_stage_cde_kernel<true>, grid, 576, k2Smem, cx.stream, p)
