@@ -170,6 +170,12 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
 // without it WG0 can get two tiles ahead, and two arrivals of the same 256 threads complete a 512-thread phase of
 // barrier 7 on their own -- the pairing is lost and WG1's last sync waits forever (seen as a hang at 4K).  (A handshake
 // in both directions at the half-tile points, by contrast, serialised the WGs and was 25 % slower.)
+#ifndef STIF_EARLY_RELEASE
+#define STIF_EARLY_RELEASE 1
+#endif
+#ifndef STIF_K1_PREFETCH
+#define STIF_K1_PREFETCH 1
+#endif
 #ifndef STIF_GATHER_TURNS
 #define STIF_GATHER_TURNS 1
 #endif
@@ -269,10 +275,23 @@ __device__ __forceinline__ void layer_finish(WgCtx& cx, uint32_t a_base, uint32_
     for (int i = 0; i < NC; ++i) {
       tmem_ld_wait();
       trace_mark(cx, 10 + i);
+      // Chunk i+2 reuses this chunk's accumulator slot and reads the SAME A operand, so all the issuer needs from us is
+      // "slot drained": arrive as soon as the accumulator is in registers, not after the epilogue.  (The epilogue's own
+      // prefetch waits for chunk i+1 -- arriving after it meant chunk i+2 could not even be issued before chunk i+1 had
+      // completed, a tensor-pipe bubble per chunk wherever the epilogue is short: the Q-table stores of the composed
+      // layer.)  The last two chunks arrive after their epilogue: those arrivals tell the issuer that the NEXT layer's A
+      // operand is complete (every warp's earlier tcgen05.st precedes them in program order).
+      const bool early = STIF_EARLY_RELEASE && i + 2 < NC;
+      if (early) {
+        tc_fence_before();
+        step_done<false>(cx);
+      }
       epi(i, v, [&]() { if (i + 1 < NC) tmem_ld32(wait_chunk(cx), v); });
       trace_mark(cx, 20 + i);
-      tc_fence_before();
-      step_done<false>(cx);   // arrive and move on: epilogue warps never wait for each other
+      if (!early) {
+        tc_fence_before();
+        step_done<false>(cx);   // arrive and move on: epilogue warps never wait for each other
+      }
       if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM, false>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));   // (counter only)
     }
   }
@@ -608,6 +627,15 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     trace_mark(cx, 1);
     // ---- stage A, first layer (hoisted): h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
     if constexpr (!ISSUER) {
+      if (STIF_K1_PREFETCH) {
+        // The stage-B gather ~10 k clocks from now reads the TB lines of this query's 2 x 2 LR footprint; asking for
+        // them now turns its exposed L2 round trips into L1 hits.  One column half asks for the upper texel row, the
+        // other for the lower one (both halves read the same 128-byte lines).
+        const int y0 = min(max(g.y.b0[jy] + CH, 0), g.H - 1), x0 = g.x.b0[jx];
+        const uint4* row = tab4 + (long)y0 * g.W * 32 + 8;
+        prefetch_l1(row + (long)min(max(x0, 0), g.W - 1) * 32);
+        prefetch_l1(row + (long)min(max(x0 + 1, 0), g.W - 1) * 32);
+      }
       const int iy = g.y.idx[jy], ix = g.x.idx[jx];
       const float rely = g.y.rel[jy], relx = g.x.rel[jx];
       const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
@@ -692,6 +720,16 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
     run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
+    if constexpr (!ISSUER) {
+      // ... and the TA line the NEXT tile of this WG starts with (its first layer otherwise opens every tile with an
+      // exposed index-table -> table-row load chain while the MUFU pipe idles)
+      const long qn = q + (long)gridDim.x * 2 * kTile;
+      if (STIF_K1_PREFETCH && CH == 0 && qn < p.q_end) {
+        const int jyn = (int)(qn / g.WW), jxn = (int)(qn - (long)jyn * g.WW);
+        const int iyn = min(max(g.y.idx[jyn], 0), g.H - 1), ixn = min(max(g.x.idx[jxn], 0), g.W - 1);
+        prefetch_l1(tab4 + ((long)iyn * g.W + ixn) * 32);
+      }
+    }
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
