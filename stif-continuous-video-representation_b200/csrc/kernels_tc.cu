@@ -173,8 +173,10 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
 #ifndef STIF_EARLY_RELEASE
 #define STIF_EARLY_RELEASE 1
 #endif
-#ifndef STIF_K1_PREFETCH
-#define STIF_K1_PREFETCH 1
+// Diagnostic builds only (results are WRONG): bit 0 drops the Q-table stores, bit 1 the TA loads, bit 2 the stage-B (TB) loads,
+// bit 3 K2's Q-table tap loads, bit 4 K2's TE tap loads -- what each memory stream costs end to end (profiles/diag_streams.sh).
+#ifndef STIF_DIAG
+#define STIF_DIAG 0
 #endif
 #ifndef STIF_GATHER_TURNS
 #define STIF_GATHER_TURNS 1
@@ -394,7 +396,7 @@ __device__ __forceinline__ void epi_store_qtab(uint32_t (&v)[32], const float* _
     o[2 * j4 + 1] = pack_half2(a1.x, a1.y);
   }
   next_ld();
-  if (!valid) return;
+  if (!valid || (STIF_DIAG & 1)) return;
   stg256(dst, o);            // two full 32-byte sectors per thread
   stg256(dst + 16, o + 8);
 }
@@ -618,24 +620,31 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
   const int ch0 = CH * 32;   // this thread's 32 channels of every 64-wide vector
 
   const long tile_first = (long)blockIdx.x * 2 + cx.wg;
-  for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
+  // (jy, jx) of this thread's query advance by a constant step from tile to tile: one 64-bit division up front
+  // instead of one per tile (and one more in the last, partial tile, whose missing rows are clamped onto the last query)
+  const long q_step = (long)gridDim.x * 2 * kTile;
+  const int jy_step = (int)(q_step / g.WW), jx_step = (int)(q_step - (long)jy_step * g.WW);
+  long q = p.q_begin + tile_first * kTile + cx.row;
+  int jy_run = (int)(q / g.WW), jx_run = (int)(q - (long)jy_run * g.WW);
+  auto next_tile = [&]() {
+    q += q_step;
+    jy_run += jy_step;
+    jx_run += jx_step;
+    if (jx_run >= g.WW) { jx_run -= g.WW; ++jy_run; }
+  };
+  for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2, next_tile()) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;   // trace the first 16 tiles only
-    const long q = p.q_begin + tile * kTile + cx.row;
     const bool valid = q < p.q_end;
-    const long qc = valid ? q : p.q_end - 1;
-    const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
+    long qc = q;
+    int jy = jy_run, jx = jx_run;
+    if (!valid) {
+      qc = p.q_end - 1;
+      jy = (int)(qc / g.WW);
+      jx = (int)(qc - (long)jy * g.WW);
+    }
     trace_mark(cx, 1);
     // ---- stage A, first layer (hoisted): h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
     if constexpr (!ISSUER) {
-      if (STIF_K1_PREFETCH) {
-        // The stage-B gather ~10 k clocks from now reads the TB lines of this query's 2 x 2 LR footprint; asking for
-        // them now turns its exposed L2 round trips into L1 hits.  One column half asks for the upper texel row, the
-        // other for the lower one (both halves read the same 128-byte lines).
-        const int y0 = min(max(g.y.b0[jy] + CH, 0), g.H - 1), x0 = g.x.b0[jx];
-        const uint4* row = tab4 + (long)y0 * g.W * 32 + 8;
-        prefetch_l1(row + (long)min(max(x0, 0), g.W - 1) * 32);
-        prefetch_l1(row + (long)min(max(x0 + 1, 0), g.W - 1) * 32);
-      }
       const int iy = g.y.idx[jy], ix = g.x.idx[jx];
       const float rely = g.y.rel[jy], relx = g.x.rel[jx];
       const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
@@ -644,7 +653,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       U8x32 ta2;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if ((j & 1) == 0) ta2 = ldg256(ta + j);
+        if ((j & 1) == 0) { if (STIF_DIAG & 2) ta2 = U8x32{}; else ta2 = ldg256(ta + j); }
         uint32_t w4[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) w4[e] = inb ? ta2.r[(j & 1) * 4 + e] : 0u;
@@ -696,7 +705,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const U8x32 v = ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
+          const U8x32 v = (STIF_DIAG & 4) ? U8x32{} : ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             gB[16 * j + 2 * e] = fma_f16((uint16_t)(v.r[e] & 0xFFFF), wq[k], gB[16 * j + 2 * e]);
@@ -720,16 +729,6 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
     run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
-    if constexpr (!ISSUER) {
-      // ... and the TA line the NEXT tile of this WG starts with (its first layer otherwise opens every tile with an
-      // exposed index-table -> table-row load chain while the MUFU pipe idles)
-      const long qn = q + (long)gridDim.x * 2 * kTile;
-      if (STIF_K1_PREFETCH && CH == 0 && qn < p.q_end) {
-        const int jyn = (int)(qn / g.WW), jxn = (int)(qn - (long)jyn * g.WW);
-        const int iyn = min(max(g.y.idx[jyn], 0), g.H - 1), ixn = min(max(g.x.idx[jxn], 0), g.W - 1);
-        prefetch_l1(tab4 + ((long)iyn * g.W + ixn) * 32);
-      }
-    }
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
                  [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
@@ -939,13 +938,16 @@ __global__ void __launch_bounds__(576, 1) k1_ensemble_kernel(const __grid_consta
 // x fp16 weight + fp32 accumulator), then sine -> bf16 -> the SW128 A tile of the first MMA.
 // K2 tile geometry: row r (0..127) of tile `tile` -> linear query index (clamped into the launch's rows / the raster so
 // that loads stay in range; `valid` says whether the query really exists).
-__device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bool& valid) {
-  const int ty = (int)(tile / p.tiles_x), tx = (int)(tile - (long)ty * p.tiles_x);
+__device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bool& valid, int& jy, int& jx) {
+  const int t32 = (int)tile;   // tiles per launch < 2^31 (a 16 K x 16 K raster has 2^21)
+  const int ty = t32 / p.tiles_x, tx = t32 - ty * p.tiles_x;
   const int patch = r >> 4, i = r & 15;
   const int y = p.row_begin + ty * 8 + (patch >> 2) * 4 + (i >> 2);
   const int x = tx * 16 + (patch & 3) * 4 + (i & 3);
   valid = (y < p.row_end) & (x < p.g.WW);
-  return (long)min(y, p.row_end - 1) * p.g.WW + min(x, p.g.WW - 1);
+  jy = min(y, p.row_end - 1);
+  jx = min(x, p.g.WW - 1);
+  return (long)jy * p.g.WW + jx;
 }
 
 // Tap staging of a warp's 16 queries lives INSIDE the warp's own 16 rows (2 KB) of the WG's A tile: query group it
@@ -960,8 +962,8 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
   {
     const int qi = lane & 15, which = lane >> 4;
     bool valid_;
-    const long q = k2_query(p, tile, warp_in_wg * 16 + qi, valid_);
-    const int jy = (int)(q / g.WW), jx = (int)(q - (long)jy * g.WW);
+    int jy, jx;
+    const long q = k2_query(p, tile, warp_in_wg * 16 + qi, valid_, jy, jx);
     const float4 fl = __ldg(reinterpret_cast<const float4*>(p.flow) + q);
     float gy, gx;
     warp_position(g, jy, jx, which ? fl.z : fl.x, which ? fl.w : fl.y, gy, gx);   // (warplayer.py:25-39)
@@ -1011,7 +1013,8 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
     const uint32_t off[8] = {oh.x, oh.y, oh.z, oh.w, ol.x, ol.y, ol.z, ol.w};
     w[0] = wq.x; w[1] = wq.y; w[2] = wq.z; w[3] = wq.w;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const uint4*>((k < 4 ? qtab_b : tab_b) + off[k]) + sub);
+    for (int k = 0; k < 8; ++k)
+      v[k] = (STIF_DIAG & (k < 4 ? 8 : 16)) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>((k < 4 ? qtab_b : tab_b) + off[k]) + sub);
   };
   __half2 acc2[4];
   // packed fp16 FMAs (2 channels per instruction, fp16 accumulate: the emulator shows the RGB error is unchanged)
@@ -1071,7 +1074,8 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
   for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2) {
     if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
     bool valid;
-    const long q = k2_query(p, tile, cx.row, valid);
+    int jy_, jx_;
+    const long q = k2_query(p, tile, cx.row, valid, jy_, jx_);
     if constexpr (!ISSUER) gather_turn_wait(cx);
 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)

@@ -70,8 +70,6 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t* a) {
                "r"(a[5]), "r"(a[6]), "r"(a[7])
                : "memory");
 }
-// ask for a global line in L1 (no register, no scoreboard: the warp does not wait for it)
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // shared::cta -> global bulk store (TMA); completion tracked with bulk groups of the issuing thread
 __device__ __forceinline__ void bulk_store_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes)
