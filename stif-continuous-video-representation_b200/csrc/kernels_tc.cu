@@ -178,6 +178,12 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
 #ifndef STIF_DIAG
 #define STIF_DIAG 0
 #endif
+// WG0 hands the gather turn over once the loads of half-step STIF_TURN_EARLY (1..8) are in flight; 9 = after the whole gather and
+// its step barrier.  Measured (K2 ms per launch at config 2): 9: 0.594, 8: 0.580, 7: 0.576-0.580, 6: 0.600, 4: 0.594 -- with all of
+// WG0's loads issued, WG1's first load batch overlaps WG0's last blend + sines instead of waiting behind them.
+#ifndef STIF_TURN_EARLY
+#define STIF_TURN_EARLY 8
+#endif
 #ifndef STIF_GATHER_TURNS
 #define STIF_GATHER_TURNS 1
 #endif
@@ -994,7 +1000,8 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
 }
 
 // phase 2 (loads + blend + sine -> A tile)
-__device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane) {
+template <class Sig>
+__device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane, Sig&& loads_issued) {
   const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
   const char* __restrict__ tab_b = reinterpret_cast<const char*>(p.tab);
   const int sub = lane & 7;
@@ -1035,6 +1042,7 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
       if (s_ & 1) load_step(s_ + 1, va, wa);
       else load_step(s_ + 1, vb, wb);
     }
+    if (s_ + 1 == STIF_TURN_EARLY) loads_issued();
     if ((s_ & 1) == 0) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc2[e] = __float2half2_rn(0.f);
@@ -1081,7 +1089,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
     trace_mark(cx, 1);
     if constexpr (!ISSUER) {
-      k2_gather_blend(p, a0, stg, warp_in_wg, lane);
+      k2_gather_blend(p, a0, stg, warp_in_wg, lane, [&]() { gather_turn_done(cx, tile == tile_first); });
       fence_proxy_async_smem();
       tc_fence_before();
     }
@@ -1089,7 +1097,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     step_done<ISSUER>(cx);
     trace_mark(cx, 3);
 
-    if constexpr (!ISSUER) gather_turn_done(cx, tile == tile_first);
+    if constexpr (!ISSUER) { if (STIF_TURN_EARLY > 8) gather_turn_done(cx, tile == tile_first); }
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
     run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
