@@ -105,52 +105,94 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- CPU reference arm
-def cpu_sample_inputs():
-    """Bounded sample of the config-2 workload for the host-core baseline: one of the two timesteps on a
-    quarter-area crop of the latent (135x240 -> 540x960 = 518 400 queries); per-query work and scale
-    factor are those of config 2."""
-    from oracle import synth
-    w = synth.make_weights(0, False)
-    lat, fr = synth.make_inputs(0, 1, 135, 240, 0.05)
-    return w, lat, fr, [0.5], (540, 960), "config2 quarter-area crop: 135x240 latent -> 540x960, t=[0.5], 518400 queries"
+CPU_SAMPLES = {
+    # name: (H, W, (HH, WW), times, description) -- per-query work and scale factor are those of config 2
+    "quarter": (135, 240, (540, 960), [0.5],
+                "config2 quarter-area crop: 135x240 latent -> 540x960, t=[0.5], 518400 queries"),
+    "full": (270, 480, (1080, 1920), [0.0, 0.5],
+             "the whole config-2 step: 270x480 latent -> 1080x1920, t=[0.0, 0.5], 4147200 queries"),
+}
 
 
-def run_cpu_port(steps: int, warmup: int):
+def run_cpu_reference(steps: int, warmup: int, sample: str = "quarter"):
+    """The reference's OWN implementation on the host cores: the unmodified `LunaTokis.decoding`
+    (Sakuya_arch_test.py:364-459) imported from the staged tree oracle/_ref (oracle/stage_ref.py), fp32, all host threads.
+    Falls back to the torch-CPU port (oracle/port_torch.py, kind "port") only if the staged tree is absent.
+    The caller must have hidden the GPUs (CUDA_VISIBLE_DEVICES="") before torch was imported: the method hard-codes
+    `.cuda()` (:372-375) and warplayer.py:5 picks its device at import."""
     import torch
-    from oracle import port_torch
+    from oracle import ref_loader, synth
+    assert not torch.cuda.is_available(), "the CPU reference arm must run with the GPUs hidden"
     torch.set_num_threads(os.cpu_count() or 1)
-    w, lat, fr, times, scale, what = cpu_sample_inputs()
+    H, W, scale, times, what = CPU_SAMPLES[sample]
+    w = synth.make_weights(0, False)
+    lat, fr = synth.make_inputs(0, 1, H, W, 0.05)
     nq = scale[0] * scale[1] * len(times)
+    if ref_loader.reference_available():
+        model = ref_loader.build_reference_model(w)
+        kind = "reference"
+        src = f"unmodified LunaTokis.decoding from {'oracle/_ref' if ref_loader.reference_kind() == 'staged' else ref_loader.REFERENCE_ROOT}"
+
+        def step():
+            ref_loader.reference_decode(lat, fr, w, times, scale, device="cpu", model=model)
+    else:
+        from oracle import port_torch
+        kind, src = "port", "oracle/port_torch.py (staged reference absent)"
+
+        def step():
+            port_torch.decode(lat, fr, w, times, scale)
     for _ in range(warmup):
-        port_torch.decode(lat, fr, w, times, scale)
+        step()
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        port_torch.decode(lat, fr, w, times, scale)
+        step()
         ts.append(time.perf_counter() - t0)
     sec = float(np.mean(ts))
-    return {"value": nq / sec, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": nq / sec, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": kind, "source": src,
             "sample": what, "sec_per_step": sec, "best_sec": float(np.min(ts))}
 
 
+def workload_config(args, world: int) -> dict:
+    """The `config` object of the JSON line -- identical for both arms (`--impl ours` / `--impl reference`)."""
+    H, W, HH, WW, times = WORKLOADS[args.workload]
+    return {"workload": f"{args.workload}: B=1 {H}x{W} latent -> {HH}x{WW}, times {times} "
+                        f"({HH * WW * len(times)} queries per rank per step); one frame pair per rank",
+            "weights": "SIREN-init seed 0" + (" stress variant" if args.stress_weights else ""),
+            "l2": "no flush: per-step working set (latent 100 MB + tables + 50 MB output) exceeds the 126 MB L2"}
+
+
 def main_reference(args):
-    """`--impl reference`: the reference algorithm on the box's host cores (torch CPU port of
-    LunaTokis.decoding, oracle/port_torch.py -- the reference itself is Python and does not travel)."""
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (oracle/_ref),
+    each step a bounded sample of the workload (`cpu_baseline.sample`).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    H, W, HH, WW, times = WORKLOADS[args.workload]
-    res = run_cpu_port(max(1, args.steps), max(1, min(args.warmup, 1)))
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""            # before torch is imported anywhere in this process
+    res = run_cpu_reference(max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample)
     line = {"impl": "reference", "metric": "decoded space-time queries/sec", "value": res["value"], "unit": "queries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {H}x{W} latent -> {HH}x{WW}, times {times}; timed on a bounded sample",
-                       "sample": res["sample"]},
-            "cpu_baseline": {"value": res["value"], "unit": "queries/s", "cores": res["cores"], "kind": "port",
-                             "sample": res["sample"]},
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": res["value"], "unit": "queries/s", "cores": res["cores"], "kind": res["kind"],
+                             "sample": res["sample"], "source": res["source"]},
             "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(sample: str, steps: int):
+    """`cpu_baseline` leg of our arm: the reference arm in a child process with the GPUs hidden (this process holds a
+    CUDA context and the reference picks its device at import)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "0",
+                        "--cpu-sample", sample], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    for ln in reversed(p.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError(f"CPU reference arm failed: {p.stderr[-2000:]}")
 
 
 # --------------------------------------------------------------------------- our arm
@@ -291,11 +333,8 @@ def main_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "bf16" else "f32",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: B=1 {H}x{W} latent -> {HH}x{WW}, times {times} "
-                                   f"({nq_rank} queries per rank per step); one frame pair per rank",
-                       "weights": "SIREN-init seed 0" + (" stress variant" if args.stress_weights else ""),
-                       "l2": "no flush: per-step working set (latent 100 MB + tables + 50 MB output) exceeds the 126 MB L2",
-                       "weight_broadcast_s": t_bcast, "mode": args.mode},
+            "config": workload_config(args, world),
+            "setup": {"weight_broadcast_s": t_bcast, "mode": args.mode},
             "roofline": roof,
             "e2e": {"value": world * nq_rank / e2e_sec, "unit": "queries/s",
                     "h2d_bytes_per_step": int(lat_p.numel() * 4 + fr_p.numel() * 4),
@@ -307,8 +346,7 @@ def main_ours(args):
             "clocks": sampler.summary(w0, w1),
             "output_checksum": checksum}
     if world == 1 and not args.no_cpu_baseline:
-        cb = run_cpu_port(args.cpu_steps, 1)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = cpu_baseline_subprocess(args.cpu_sample if args.cpu_sample != "quarter" else "full", args.cpu_steps)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -324,7 +362,9 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--stress-weights", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=1)
+    ap.add_argument("--cpu-sample", default="quarter", choices=sorted(CPU_SAMPLES),
+                    help="bounded sample one CPU step covers (reference arm; our arm's cpu_baseline leg times 'full' once)")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

@@ -22,7 +22,8 @@
  *     ordinary host memory.  There is NO CPU fallback: without a usable sm_100 device
  *     stif_create fails with STIF_ENODEV.
  *   - all work is stream-ordered on the cudaStream_t passed as `void* stream`
- *     (NULL = legacy default stream).  A handle is not re-entrant.
+ *     (NULL = legacy default stream), except the one-off table upload on first sight of a geometry
+ *     (see stif_prepare).  A handle is not re-entrant.
  *   - the caller owns every buffer, including the workspace; the library owns only its
  *     packed copy of the weights and a few KB of per-geometry axis tables.
  */
@@ -92,6 +93,15 @@ int stif_destroy(stif_decoder_t* dec);
  * The library folds omega_0 = 30 (SIREN.py:45) into its packed copy and synchronises the
  * device before returning, so the host buffers may be freed immediately. */
 int stif_load_weights(stif_decoder_t* dec, const float* const* tensors_host, int num_tensors);
+
+/* Build and cache the per-geometry axis tables of an [H,W] -> [HH,WW] decode (plus the shifted tables of
+ * STIF_FLAG_LOCAL_ENSEMBLE / the coordinate warp base of STIF_FLAG_WARP_FROM_COORD if `mode` carries the flag) ahead of
+ * time.  Optional: the first stif_decode of a geometry does this itself, but that first call then contains a cudaMalloc
+ * and a synchronous upload (a device-wide sync; illegal inside a stream capture) before its stream-ordered work.  After
+ * stif_prepare -- or after any earlier decode of the same geometry -- stif_decode / stif_decode_rows are purely
+ * stream-ordered.  The cache holds 64 geometries; the oldest one is evicted (the reference's own warp-grid cache,
+ * warplayer.py:6,26-33, grows without bound). */
+int stif_prepare(stif_decoder_t* dec, int H, int W, int HH, int WW, int mode);
 
 /* Bytes of device workspace stif_decode needs for this problem (0 on invalid arguments). */
 size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode);

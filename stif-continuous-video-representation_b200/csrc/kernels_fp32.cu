@@ -207,10 +207,12 @@ __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* 
     Taps lr = make_taps(gy, gx, g.H, g.W);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (hr.w[k] != 0.f) {
-        int row = hr.off[k] / g.WW;
-        if (row < band_lo || row >= band_hi) { if (c == 0) atomicOr(flag, 1); continue; }
-      }
+      // A zero-weight tap (out-of-grid taps are redirected to row 0; exact-integer positions give in-grid taps with w == 0)
+      // may point at a Q-table row this row-band launch never wrote: 0 x stale NaN bits is NaN, so the load is skipped,
+      // as the tensor-core path does (kernels_tc.cu, k2_gather_taps).
+      if (hr.w[k] == 0.f) continue;
+      const int row = hr.off[k] / g.WW;
+      if (row < band_lo || row >= band_hi) { if (c == 0) atomicOr(flag, 1); continue; }
       s = fmaf(hr.w[k], qtab[(long)hr.off[k] * 128 + wv * 64 + c], s);
     }
 #pragma unroll

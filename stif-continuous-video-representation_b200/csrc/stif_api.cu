@@ -79,6 +79,7 @@ struct stif_decoder {
   DeviceWeights32 w32{};
   TcWeights* tcw = nullptr;
   std::map<std::array<int, 5>, DeviceGeometry> geos;   // key: H, W, HH, WW, warp-base variant
+  std::vector<std::array<int, 5>> geo_order;           // insertion order of `geos` (oldest first): single-entry eviction
   int64_t launches = 0;
   // last decoded slab (debug introspection)
   const float* last_flow = nullptr;
@@ -182,14 +183,18 @@ int get_geometry(stif_decoder* d, int H, int W, int HH, int WW, cudaStream_t str
                      (const float*)(b + xo + 3 * nx), (const float*)(b + xo + 4 * nx), nullptr};
     g.half_h = (float)((HH - 1.0) / 2.0);  // python double -> fp32 at the tensor division (warplayer.py:35-36)
     g.half_w = (float)((WW - 1.0) / 2.0);
-    if (d->geos.size() > 64) {  // bounded cache (the reference's warp-grid cache is unbounded, warplayer.py:6)
-      for (auto& kv : d->geos) {
-        cudaFree(kv.second.blob);
-        for (void* eb : kv.second.ens_blob) if (eb) cudaFree(eb);
-      }
-      d->geos.clear();
+    // bounded cache (the reference's warp-grid cache is unbounded, warplayer.py:6): drop the OLDEST geometry only.
+    // cudaFree synchronises the device, so no kernel still reads the evicted tables.
+    while (d->geos.size() >= 64 && !d->geo_order.empty()) {
+      auto old = d->geos.find(d->geo_order.front());
+      d->geo_order.erase(d->geo_order.begin());
+      if (old == d->geos.end()) continue;
+      cudaFree(old->second.blob);
+      for (void* eb : old->second.ens_blob) if (eb) cudaFree(eb);
+      d->geos.erase(old);
     }
     it = d->geos.emplace(key, dg).first;
+    d->geo_order.push_back(key);
   }
   *out = &it->second.geo;
   (void)stream;
@@ -231,12 +236,35 @@ struct ScopedSpan {  // brackets one kernel group with events when profiling is 
   stif_decoder* d; cudaStream_t s; cudaEvent_t b = nullptr;
   ScopedSpan(stif_decoder* d_, cudaStream_t s_, int kind) : d(d_), s(s_) {
     if (!d->profiling) return;
+    if (d->spans.size() >= 16384) {   // nobody is reading (stif_profile_read): recycle the oldest half instead of growing
+      for (size_t i = 0; i < 8192; ++i) { d->event_pool.push_back(d->spans[i].a); d->event_pool.push_back(d->spans[i].b); }
+      d->spans.erase(d->spans.begin(), d->spans.begin() + 8192);
+    }
     cudaEvent_t a = take_event(d);
     b = take_event(d);
     cudaEventRecord(a, s);
     d->spans.push_back({a, b, kind});
   }
   ~ScopedSpan() { if (b) cudaEventRecord(b, s); }
+};
+
+// Error exits of the host pipelines: async copies to / from the CALLER's host buffers may still be in flight on the
+// copy streams when a later call fails.  The guard drains all three streams before the error code is returned (the caller
+// may free its buffers right after) and hands every event of the call back to the pool on every exit.
+struct PipeGuard {
+  stif_decoder* d;
+  cudaStream_t compute, h2d, d2h;
+  std::vector<cudaEvent_t>* used;
+  bool ok = false;
+  ~PipeGuard() {
+    if (!ok) {
+      if (h2d) cudaStreamSynchronize(h2d);
+      cudaStreamSynchronize(compute);
+      if (d2h) cudaStreamSynchronize(d2h);
+    }
+    for (auto e : *used) d->event_pool.push_back(e);
+    used->clear();
+  }
 };
 
 // stif_decode_host: host<->device copies pipelined with the kernels.  The latent is uploaded in row
@@ -291,6 +319,7 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
   const std::vector<int>&he = plan.he, &ge = plan.ge, &lr_end = plan.lr_end;
   const int nbands = (int)he.size();
   std::vector<cudaEvent_t> used_events;
+  PipeGuard guard{d, stream, hp.h2d, hp.d2h, &used_events};
   auto chain = [&](cudaStream_t from, cudaStream_t to) -> cudaError_t {   // `to` waits for what `from` holds now
     cudaEvent_t ev = take_event(d);
     used_events.push_back(ev);
@@ -421,7 +450,7 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
         fprintf(stderr, "   (HR rows A+B < %d, C-E < %d)\n", he[k], ge[k]);
       }
   }
-  for (auto e : used_events) d->event_pool.push_back(e);
+  guard.ok = true;
   const Workspace last = slab_ws(T <= G ? T - 1 : 0);
   d->last_flow = last.flow;
   d->last_flow_floats = Q * 4;
@@ -450,6 +479,11 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
     return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT with STIF_MODE_BF16 needs the full x4 raster (HH = 4H, WW = 4W); use STIF_MODE_FP32 otherwise");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
+  // The tensor-core K2 gather stages tap addresses as 32-bit BYTE offsets (256 B per HR pixel, 512 B per LR texel,
+  // kernels_tc.cu k2_gather_taps): they wrap above 2^24 HR pixels / 2^23 LR texels.  Refuse instead of gathering wrong rows.
+  if (prec == STIF_MODE_BF16 && ((long long)HH * WW > (1ll << 24) || (long long)H * W >= (1ll << 23)))
+    return set_error(STIF_EINVAL, "raster too large for STIF_MODE_BF16 (HH*WW=%lld > 2^24 or H*W=%lld >= 2^23); decode it in row-band "
+                     "sized pieces of a smaller raster or use STIF_MODE_FP32", (long long)HH * WW, (long long)H * W);
   if (row_begin < 0 || row_end > HH || row_begin >= row_end || halo < 0)
     return set_error(STIF_EINVAL, "invalid row band [%d,%d) halo %d for HH=%d", row_begin, row_end, halo, HH);
   const size_t need = stif_workspace_bytes(B, H, W, HH, WW, T, mode);
@@ -465,6 +499,8 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   const size_t Q = (size_t)HH * WW;
   CUDA_OR_RETURN(cudaMemsetAsync(ws.flag, 0, sizeof(int), stream));
   std::vector<cudaEvent_t> used_events;
+  PipeGuard guard{d, stream, hp ? hp->h2d : nullptr, hp ? hp->d2h : nullptr, &used_events};
+  if (!hp) guard.ok = true;   // device-buffer calls are purely stream-ordered: nothing of the caller's to drain
   const int nbands = hp ? std::max(1, std::min(hp->bands, H)) : 1;
   const size_t plane = (size_t)H * W;
   for (int b = 0; b < B; ++b) {
@@ -531,7 +567,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (hp) {
     CUDA_OR_RETURN(cudaStreamSynchronize(hp->d2h));
     CUDA_OR_RETURN(cudaStreamSynchronize(stream));
-    for (auto e : used_events) d->event_pool.push_back(e);
+    guard.ok = true;
   }
   d->last_flow = ws.flow;
   d->last_flow_floats = Q * 4;
@@ -632,6 +668,19 @@ int stif_load_weights(stif_decoder_t* d, const float* const* tensors, int num_te
 size_t stif_workspace_bytes(int B, int H, int W, int HH, int WW, int T, int mode) {
   if (B < 1 || H < 1 || W < 1 || HH < 1 || WW < 1 || T < 1) return 0;
   return carve_workspace(nullptr, H, W, HH, WW, mode).total_bytes;
+}
+
+int stif_prepare(stif_decoder_t* d, int H, int W, int HH, int WW, int mode) {
+  if (!d) return set_error(STIF_EINVAL, "null decoder");
+  if (int rc = check_shape(1, H, W, HH, WW, 1)) return rc;
+  CUDA_OR_RETURN(cudaSetDevice(d->device));
+  const Geometry* geo = nullptr;
+  if (int rc = get_geometry(d, H, W, HH, WW, nullptr, &geo, (mode & STIF_FLAG_WARP_FROM_COORD) != 0)) return rc;
+  if (mode & STIF_FLAG_LOCAL_ENSEMBLE) {
+    DeviceGeometry* dg = nullptr;
+    if (int rc = get_ensemble_geometry(d, H, W, HH, WW, &dg)) return rc;
+  }
+  return STIF_OK;
 }
 
 int stif_decode(stif_decoder_t* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,

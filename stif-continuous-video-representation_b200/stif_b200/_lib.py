@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "lib", "libstif_b200.so"))
+# STIF_LIB selects another in-tree build of the same library (tuning variants under build_variants/); there is still no
+# fallback -- the named file must exist.
+LIB_PATH = os.path.abspath(os.environ["STIF_LIB"]) if os.environ.get("STIF_LIB") else \
+    os.path.normpath(os.path.join(_HERE, "..", "lib", "libstif_b200.so"))
 
 STIF_OK = 0
 STIF_MODE_BF16 = 0
@@ -24,7 +27,7 @@ STIF_ABI_VERSION = 1
 # every symbol include/stif_b200.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
-    "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_axis_tables",
+    "stif_prepare", "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_axis_tables",
     "stif_ensemble_weights", "stif_debug_last_flow", "stif_debug_host_pipeline", "stif_debug_band_plan", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
 ]
 
@@ -45,6 +48,7 @@ def _load():
     lib.stif_create.argtypes = [C.POINTER(vp), C.c_int]
     lib.stif_destroy.argtypes = [vp]
     lib.stif_load_weights.argtypes = [vp, C.POINTER(vp), C.c_int]
+    lib.stif_prepare.argtypes = [vp] + [C.c_int] * 5
     lib.stif_workspace_bytes.argtypes = [C.c_int] * 7
     lib.stif_workspace_bytes.restype = C.c_size_t
     lib.stif_decode.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int,

@@ -164,7 +164,8 @@ class STIFQueryDecoder(torch.nn.Module):
         ws = self._workspace_for(B, H, W, HH, WW, T, m)
         shape, dtype = ((T, B, HH, WW, 3), torch.uint8) if uint8 else ((T, B, 3, HH, WW), torch.float32)
         if out is None:
-            out = torch.empty(shape, dtype=dtype, device=self.device)
+            # a row-band call writes only its band: the other rows are defined (zero), not allocator garbage
+            out = (torch.zeros if rows is not None else torch.empty)(shape, dtype=dtype, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
             raise ValueError(f"out must be a contiguous {dtype} {list(shape)} tensor")
         stream = torch.cuda.current_stream(self.device).cuda_stream
@@ -393,6 +394,8 @@ def install_class_patch(luna_tokis_cls, mode: str = "bf16"):
         return _dec(self).decode(self.feat, self.inp, times, scale)
 
     def decoding_fasttest(self, times=None, scale=None):
+        if self.feat.shape[0] != 1:
+            raise ValueError("decoding_fasttest requires batch size 1 (Sakuya_arch_test.py:877)")
         return _dec(self).decode_stacked(self.feat, self.inp, list(times), scale)[:, 0]
 
     def decoding_localensemble(self, times=None, scale=None):

@@ -538,3 +538,72 @@ def test_drop_in_patch_rebinds_every_decode_method(how, stif):
     assert np.abs(torch.stack(tst, 0).cpu().numpy() - gt["rgb"]).max() <= 1e-4
     win = model.decoding_memory(times, (100, 90), np.array([0.1, -0.2]), input_img=None)
     assert isinstance(win, list) and win[0].shape == (1, 3, 64, 64)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_row_band_with_nan_prefilled_workspace(mode, stif):
+    """A row-band decode must not read Q-table rows it never wrote, even through zero-weight taps (0 x NaN = NaN): the
+    workspace is pre-filled with 0xFF bytes (NaN in fp32 and fp16) and the band must still equal the full decode.  Exact
+    integer warp positions (zero flow at x4 hits them for the linspace base's end points) and out-of-grid taps both occur."""
+    lat, fr = synth.smooth_inputs(21, 1, 24, 20, 0.05)
+    w = synth.make_weights(0, False)                     # init weights: flows ~ +-0.1 px, many taps with tiny / zero weights
+    dec = stif.STIFQueryDecoder(0, mode=mode)
+    dec.load_weights(w)
+    latc, frc = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    full = dec.decode_stacked(latc, frc, [0.5], None)
+    torch.cuda.synchronize()
+    for rows in ((32, 56), (0, 16), (80, 96)):
+        dec._workspace.fill_(0xFF)
+        band = dec.decode_stacked(latc, frc, [0.5], None, rows=rows, halo=8)
+        torch.cuda.synchronize()
+        got = band[0, 0, :, rows[0]:rows[1]]
+        assert torch.isfinite(got).all(), rows
+        assert torch.equal(got, full[0, 0, :, rows[0]:rows[1]]), rows
+        assert float(band[0, 0, :, :rows[0]].abs().max() if rows[0] else 0.0) == 0.0     # rows outside the band: zeros
+    dec.close()
+
+
+def test_bf16_rejects_rasters_beyond_32bit_tap_offsets(stif):
+    """The tensor-core K2 stages tap addresses as 32-bit byte offsets: HH*WW > 2^24 (or H*W >= 2^23) must be refused with
+    STIF_EINVAL, not decoded wrongly.  The check precedes every buffer access, so dummy pointers suffice."""
+    import ctypes as C
+    from stif_b200 import _lib
+    dec = stif.STIFQueryDecoder(0, mode="bf16")
+    dec.load_weights(synth.make_weights(0, False))
+    dummy = torch.zeros(64, device="cuda")
+    t = (C.c_float * 1)(0.5)
+    args = lambda HH, WW, mode: (dec._handle, dummy.data_ptr(), dummy.data_ptr(), 1, 8, 8, HH, WW, t, 1, mode, dummy.data_ptr(), 256,
+                                 dummy.data_ptr(), None)
+    rc = _lib.lib.stif_decode(*args(4097, 4096, _lib.STIF_MODE_BF16))
+    assert rc == -1 and b"too large for STIF_MODE_BF16" in _lib.lib.stif_last_error()
+    rc = _lib.lib.stif_decode(*args(4096, 4096, _lib.STIF_MODE_BF16))          # exactly 2^24: allowed (fails later: workspace)
+    assert rc == -4, _lib.lib.stif_last_error()
+    rc = _lib.lib.stif_decode(*args(4097, 4096, _lib.STIF_MODE_FP32))          # the fp32 path indexes with 64 bits
+    assert rc == -4, _lib.lib.stif_last_error()
+    dec.close()
+
+
+def test_prepare_makes_decode_stream_ordered(stif):
+    """After stif_prepare the decode of a new geometry can be captured in a CUDA graph (no allocation / sync inside)."""
+    from stif_b200 import _lib
+    dec = stif.STIFQueryDecoder(0, mode="bf16")
+    w = synth.make_weights(0, True)
+    dec.load_weights(w)
+    lat, fr = synth.smooth_inputs(3, 1, 20, 28, 0.05)
+    latc, frc = torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda()
+    _lib.check(_lib.lib.stif_prepare(dec._handle, 20, 28, 80, 112, _lib.STIF_MODE_BF16))
+    out = torch.empty((1, 1, 3, 80, 112), device="cuda")
+    dec._workspace_for(1, 20, 28, 80, 112, 1, _lib.STIF_MODE_BF16)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            dec.decode_stacked(latc, frc, [0.25], (80, 112), out=out)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    ref = dec.decode_stacked(latc, frc, [0.25], (80, 112))
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    dec.close()
