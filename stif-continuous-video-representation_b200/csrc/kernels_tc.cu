@@ -204,6 +204,50 @@ __device__ __forceinline__ void gather_turn_done(const WgCtx& cx, bool first_til
   }
 }
 
+// ---- sine turns ------------------------------------------------------------------------------------------------------
+// The two workgroups share one MUFU pipe per SM sub-partition.  Left alone they run in LOCKSTEP (same phase of their tiles
+// at the same time): both burn sines together, each at half rate, and both then sit in the same MMA wait / gather / store
+// phase with the MUFU idle -- a tile costs 2 S + N clocks (S = its sine time alone, N = everything else), measured.  The
+// sine-heavy phases ("BIG": the four-chunk 64->256 layers, 2 x 256 of K1's 768 sines per query; K2: 64->256 + 256->256,
+// 512 of 640; STIF_K2_SINE_TURNS = 1: those two layers as one phase, 2: as two phases, 3: all three hidden layers as one)
+// are therefore taken in turns: a token alternates WG0 -> WG1 -> WG0 ..., so the holder's sines run at the
+// full MUFU rate while the other WG does its MMA waits, gathers, Q-table stores and small layers underneath: S + N.
+// Named barriers A (WG0's 256 epilogue threads arrive, WG1's sync) and B (roles swapped); every arrival is consumed by
+// exactly one sync before the next arrival on the same barrier can happen (the arriving WG needs the other barrier's
+// hand-back first), and nobody waits for an arrival that is never made: WG0 owns tile 2b + 2Gj, WG1 tile 2b + 1 + 2Gj of
+// round j, so WG1's rounds are a prefix of WG0's and "does my partner have this / the next round" is a tile-index test.
+#ifndef STIF_K1_SINE_TURNS
+#define STIF_K1_SINE_TURNS 0
+#endif
+#ifndef STIF_K2_SINE_TURNS
+#define STIF_K2_SINE_TURNS 0
+#endif
+template <int BAR_A, int BAR_B>
+struct SineTurn {
+  int wg;
+  bool first_round;     // WG0: no hand-back to take before the very first phase
+  bool partner_now;     // WG0: WG1 has a tile in this round
+  bool partner_next;    // WG1: WG0 has a tile in the next round
+  // phase s of NPH phases per round
+  template <int NPH>
+  __device__ __forceinline__ void acquire(int s) const {
+    if (wg == 0) {
+      const bool take = s > 0 ? partner_now : !first_round;
+      if (take) asm volatile("bar.sync %0, 512;" ::"n"(BAR_B) : "memory");
+    } else {
+      asm volatile("bar.sync %0, 512;" ::"n"(BAR_A) : "memory");
+    }
+  }
+  template <int NPH>
+  __device__ __forceinline__ void release(int s) const {
+    if (wg == 0) {
+      if (partner_now) asm volatile("bar.arrive %0, 512;" ::"n"(BAR_A) : "memory");
+    } else {
+      if (s + 1 < NPH || partner_next) asm volatile("bar.arrive %0, 512;" ::"n"(BAR_B) : "memory");
+    }
+  }
+};
+
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the warp in hardware for a bounded time, so this loop turns only a few times per wait; the
   // iteration cap converts a lost arrival into a launch failure instead of a hung GPU.
@@ -648,6 +692,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       jy = (int)(qc / g.WW);
       jx = (int)(qc - (long)jy * g.WW);
     }
+    SineTurn<7, 8> turn{cx.wg, tile == tile_first, tile + 1 < ntiles, tile - 1 + (long)gridDim.x * 2 < ntiles};
     trace_mark(cx, 1);
     // ---- stage A, first layer (hoisted): h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
     if constexpr (!ISSUER) {
@@ -683,7 +728,9 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if (STIF_K1_SINE_TURNS && i == 0) turn.template acquire<2>(0);
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
+      if (STIF_K1_SINE_TURNS && i == 3) turn.template release<2>(0);
     });
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
@@ -736,8 +783,11 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
-                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if (STIF_K1_SINE_TURNS && i == 0) turn.template acquire<2>(1);
+      epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf);
+      if (STIF_K1_SINE_TURNS && i == 3) turn.template release<2>(1);
+    });
     // combine the two column halves and store
     if constexpr (ISSUER) continue;
     const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
@@ -1098,11 +1148,16 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     trace_mark(cx, 3);
 
     if constexpr (!ISSUER) { if (STIF_TURN_EARLY > 8) gather_turn_done(cx, tile == tile_first); }
+    SineTurn<9, 10> turn{cx.wg, tile == tile_first, tile + 1 < ntiles, tile - 1 + (long)gridDim.x * 2 < ntiles};
     // ---- encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe       (:456-457)
-    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
-                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
+    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; }, [&](int, uint32_t(&v)[32], auto&& pf) {
+      if (STIF_K2_SINE_TURNS == 3) turn.template acquire<1>(0);
+      epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf);
+    });
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if ((STIF_K2_SINE_TURNS == 1 || STIF_K2_SINE_TURNS == 2) && i == 0) turn.template acquire<STIF_K2_SINE_TURNS>(0);
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
+      if (STIF_K2_SINE_TURNS == 2 && i == 3) turn.template release<2>(0);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     layer_begin<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
@@ -1110,8 +1165,11 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
       const long tile_next = tile + (long)gridDim.x * 2;
       if (tile_next < ntiles && !ISSUER) k2_gather_taps<BAND>(p, stg, tile_next, warp_in_wg, lane);
     }
-    layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
-                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf); });
+    layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if (STIF_K2_SINE_TURNS == 2 && i == 0) turn.template acquire<2>(1);
+      epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf);
+      if (STIF_K2_SINE_TURNS && i == 3) turn.template release<(STIF_K2_SINE_TURNS == 2 ? 2 : 1)>(STIF_K2_SINE_TURNS == 2 ? 1 : 0);
+    });
     if constexpr (ISSUER) continue;
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
