@@ -195,6 +195,67 @@ def cpu_baseline_subprocess(sample: str, steps: int):
     raise RuntimeError(f"CPU reference arm failed: {p.stderr[-2000:]}")
 
 
+# --------------------------------------------------------------------------- sharded (strong-scaling) leg
+SHARDED_JOBS = {
+    # BASELINE.json config 4: 4K output, x8 temporal; 8 (t) slabs -> one per GPU at N=8, round-robin below
+    "config4": (1, 540, 960, (2160, 3840), [i / 8.0 for i in range(8)]),
+    # config 2 split across the GPUs: 2 slabs -> whole slabs at N<=2, row bands with a locally recomputed halo above
+    "config2": (1, 270, 480, (1080, 1920), [0.0, 0.5]),
+}
+
+
+def sharded_leg(job: str, steps: int, world: int, rank: int, weights, mode: str, maxreduce, barrier) -> dict:
+    """The north-star multi-GPU split: ONE job whose queries are partitioned over the N ranks by the query-sharding
+    launcher (stif_b200/launcher.py) -- latent + frames + weights broadcast once from rank 0 over NCCL (timed apart,
+    `broadcast_s`), then every rank decodes its (pair, t) slabs / row bands with no collective inside the loop.  Total work
+    is fixed, so this is STRONG scaling.  The checksum is an exact integer sum over the fp32 bit patterns of every
+    unit's rows: identical at every N iff the sharded result is bit-identical to the single-GPU decode."""
+    import torch
+    import torch.distributed as dist
+    from stif_b200 import synthetic as synth
+    from stif_b200.launcher import QueryShardLauncher, plan_units
+
+    P, H, W, out_size, times = SHARDED_JOBS[job]
+    launcher = QueryShardLauncher(mode=mode)
+    lat = fr = None
+    if rank == 0:
+        lat_np, fr_np = synth.make_inputs(200, P, H, W, 0.05)
+        lat, fr = torch.from_numpy(lat_np).cuda(), torch.from_numpy(fr_np).cuda()
+    barrier()
+    tb = time.perf_counter()
+    launcher.broadcast_weights(weights if rank == 0 else None)
+    launcher.broadcast_inputs(lat, fr, (P, H, W))
+    torch.cuda.synchronize()
+    t_bcast = maxreduce(time.perf_counter() - tb)
+    for _ in range(2):
+        results = launcher.decode(times, out_size, halo=16)
+    del results
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        results = launcher.decode(times, out_size, halo=16)
+    ev1.record()
+    barrier()
+    ms = maxreduce(ev0.elapsed_time(ev1) / steps)
+    local_sum = 0
+    for u, t in results:
+        local_sum += int(t[:, u.row_begin:u.row_end].contiguous().view(torch.int32).to(torch.int64).sum().item())
+    tot = torch.tensor([local_sum], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    units = plan_units(P, len(times), out_size[0], world)
+    nq = P * len(times) * out_size[0] * out_size[1]
+    kind = "slabs" if all(u.row_begin == 0 and u.row_end == out_size[0] for u in units) else "row bands + local halo"
+    launcher._decoder.close()
+    del launcher, results
+    torch.cuda.empty_cache()
+    return {"workload": f"{job}: {P} pair(s) {H}x{W} latent -> {out_size[0]}x{out_size[1]}, {len(times)} timesteps = {nq} queries in total",
+            "scaling": "strong", "value": nq / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "units": len(units),
+            "partition": kind, "broadcast_s": t_bcast, "collectives_in_decode_loop": 0,
+            "checksum_i64": int(tot.item())}
+
+
 # --------------------------------------------------------------------------- our arm
 def main_ours(args):
     import torch
@@ -300,6 +361,14 @@ def main_ours(args):
     barrier()
     if rank == 0:
         sampler.stop()
+    # ---- the same decoder behind the query-sharding launcher: ONE job split over the N GPUs (strong scaling)
+    dec.close()
+    del lat, fr, out
+    torch.cuda.empty_cache()
+    sharded = {}
+    if not args.no_sharded:
+        for job in ("config4", "config2"):
+            sharded[job] = sharded_leg(job, max(3, args.steps // 2), world, rank, weights, args.mode, maxreduce, barrier)
 
     if rank != 0:
         if world > 1:
@@ -342,6 +411,7 @@ def main_ours(args):
                     "api": "stif_decode_host (C ABI) on pinned host buffers"},
             "e2e_uint8": {"value": world * nq_rank / e2e8_sec, "unit": "queries/s", "d2h_bytes_per_step": int(out8_p.numel()),
                           "ms_per_step": e2e8_sec * 1e3, "api": "stif_decode_host with STIF_FLAG_OUT_U8 (custom_video_test.py:102 conversion on device)"},
+            "sharded": sharded,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(w0, w1),
             "output_checksum": checksum}
@@ -362,6 +432,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--stress-weights", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the strong-scaling legs (config 4 / config 2 split over the ranks)")
     ap.add_argument("--cpu-steps", type=int, default=1)
     ap.add_argument("--cpu-sample", default="quarter", choices=sorted(CPU_SAMPLES),
                     help="bounded sample one CPU step covers (reference arm; our arm's cpu_baseline leg times 'full' once)")

@@ -131,6 +131,7 @@ struct WgCtx {
   int wg, tid_wg, warp_in_wg, row, colhalf;
   int slot;            // logical warp slot: 0..15 epilogue warps (WG0 then WG1), 16/17 the issuers (trace rows, per-warp smem)
   bool issuer;         // this warp only issues the WG's MMAs (warps 0, 1); the other 8 warps of the WG only run epilogues
+  uint64_t* extra_commit;   // issuer only: a second mbarrier the next chunk's tcgen05.commit also arrives on ("operand tile read")
   long long* trace;    // this thread's trace cursor (null unless tracing)
 };
 
@@ -219,6 +220,9 @@ __device__ __forceinline__ void gather_turn_done(const WgCtx& cx, bool first_til
 #ifndef STIF_K1_SINE_TURNS
 #define STIF_K1_SINE_TURNS 0
 #endif
+#ifndef STIF_K2_PRODUCER
+#define STIF_K2_PRODUCER 0
+#endif
 #ifndef STIF_K2_SINE_TURNS
 #define STIF_K2_SINE_TURNS 0
 #endif
@@ -284,6 +288,7 @@ __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t
         else umma_ts(d, a_base + 8 * j, bdesc, idesc, j > 0);
       }
       umma_commit(&cx.full[slot]);
+      if (cx.extra_commit) umma_commit(cx.extra_commit);
     }
     __syncwarp();
     trace_mark(cx, 41);
@@ -490,9 +495,10 @@ __device__ __forceinline__ void epi_flow_first_layer(uint32_t (&v)[32], uint32_t
 
 // ---- common prologue / epilogue of the kernels -----------------------------------------------------
 struct CtaSetup {
-  uint64_t* bars;  // [0] weights landed, [1,2] WG0 slots, [3,4] WG1 slots
+  uint64_t* bars;  // [0] weights landed, [1,2] WG0 slots, [3,4] WG1 slots, [5,6] / [7,8] producer hand-shake (see cta_prologue)
   uint32_t tmem_base;
 };
+constexpr int kProducerWarps = 4, kProducerThreads = kProducerWarps * 32;
 
 // Programmatic dependent launch: every kernel lets its successor in the stream be scheduled at once (its CTAs take SMs
 // as ours retire and run their prologue -- barrier init, TMEM allocation, the weight image's TMA load -- early), and
@@ -507,10 +513,14 @@ __device__ __forceinline__ CtaSetup cta_prologue(uint32_t bars_off, uint32_t w_o
   pdl_launch_dependents();
   if ((smem_u32(smem) & 1023u) != 0) __trap();   // SW128 operands assume a 1024-byte aligned window
   s.bars = reinterpret_cast<uint64_t*>(smem + bars_off);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bars_off + 64);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + bars_off + 120);
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i <= 4; ++i) mbar_init(&s.bars[i], 1);
+    // producer kernels: [5,6] "first-layer tile of WG0 / WG1 is complete" (every producer thread arrives),
+    //                   [7,8] "... has been read by its MMAs" (one tcgen05.commit arrives)
+    for (int i = 5; i <= 6; ++i) mbar_init(&s.bars[i], kProducerThreads);
+    for (int i = 7; i <= 8; ++i) mbar_init(&s.bars[i], 1);
     fence_mbar_init();
   }
   if (tid < 32) {
@@ -538,6 +548,9 @@ __device__ __forceinline__ void cta_epilogue(uint32_t tmem_base, uint32_t tmem_c
   if (threadIdx.x < 32) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// EW0 = index of the first epilogue warp: 2 in the 18-warp kernels (warps 0, 1 issue), 4 in the producer kernels (warps 0, 1
+// issue, 2, 3 idle so that the epilogue warps start on a warpgroup boundary, 4..19 epilogue, 20..23 produce)
+template <int EW0 = 2>
 __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   WgCtx cx;
   const int tid = threadIdx.x;
@@ -547,7 +560,7 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   // scheduler: with the issuers last (warps 16, 17) the greedy-then-oldest pick starved them behind four always-ready
   // epilogue warps -- ~2400 clocks between "accumulator slot free" and the next chunk's first tcgen05.mma.
   cx.issuer = warp < 2;
-  const int ew = warp - 2;                   // epilogue warp 0..15
+  const int ew = warp - EW0;                 // epilogue warp 0..15
   cx.wg = cx.issuer ? warp : ew >> 3;
   const int warp_in_wg = ew & 7;
   cx.slot = cx.issuer ? 16 + warp : ew;
@@ -561,6 +574,7 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   cx.full = s.bars + 1 + 2 * cx.wg;
   cx.n_issued = cx.n_waited = cx.n_steps = 0;
   cx.trace = nullptr;
+  cx.extra_commit = nullptr;
   return cx;
 }
 
@@ -729,8 +743,10 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
                  [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
       if (STIF_K1_SINE_TURNS && i == 0) turn.template acquire<2>(0);
+      if (i == 0) trace_mark(cx, 50);
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
       if (STIF_K1_SINE_TURNS && i == 3) turn.template release<2>(0);
+      if (i == 3) trace_mark(cx, 51);
     });
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F (F last: its epilogue overwrites h2)
@@ -785,8 +801,10 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
       if (STIF_K1_SINE_TURNS && i == 0) turn.template acquire<2>(1);
+      if (i == 0) trace_mark(cx, 52);
       epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf);
       if (STIF_K1_SINE_TURNS && i == 3) turn.template release<2>(1);
+      if (i == 3) trace_mark(cx, 53);
     });
     // combine the two column halves and store
     if constexpr (ISSUER) continue;
@@ -1201,6 +1219,120 @@ __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_const
   cta_epilogue(s.tmem_base, 512);
 }
 
+
+// ---- K2 with producer warps (STIF_K2_PRODUCER) -------------------------------------------------------------------------
+// 768 threads: warps 0, 1 issue, 2, 3 idle, 4..19 = the two epilogue workgroups, 20..23 = PRODUCERS.  The producers own stage
+// C + D and the hoisted first layer: warp position, bilinear footprints, the 16 tap loads per query, blend, sine, and the
+// bf16 SW128 A tile of the first MMA -- for WG0's and WG1's tiles alternately, running up to a tile ahead of the epilogue
+// workgroups, whose critical path (MMA round trips + sines) no longer contains the gather: it was 36 % of it.
+// Hand-shake per workgroup: bars[5 + wg] "A tile complete" (all 128 producer threads arrive after fence.proxy.async;
+// the WG's issuer waits for it before the first layer's MMAs), bars[7 + wg] "A tile read" (tcgen05.commit of those MMAs;
+// the producers wait for it before they overwrite the tile -- one tile of slack per WG with a single buffer, because the
+// first layer is the first thing a tile does).
+template <bool BAND>
+__device__ __forceinline__ void k2_producer_loop(const K2Params& p, const CtaSetup& s, int pw, int lane) {
+  const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
+  uint64_t* a_full = s.bars + 5;
+  uint64_t* a_empty = s.bars + 7;
+  uint32_t round = 0;
+  for (long base = (long)blockIdx.x * 2; base < ntiles; base += (long)gridDim.x * 2, ++round) {
+#pragma unroll 1
+    for (int wg = 0; wg < 2; ++wg) {
+      const long tile = base + wg;
+      if (tile >= ntiles) break;
+      uint8_t* a0 = smem + k2A0 + wg * 16384;
+      if (round > 0) mbar_wait_or_trap(&a_empty[wg], (round - 1) & 1);
+      // this warp stands in for two of the eight gather warps of the 18-warp kernel: tile rows [32 pw, 32 pw + 32)
+      uint4* stg0 = reinterpret_cast<uint4*>(a0 + (2 * pw) * 2048);
+      uint4* stg1 = reinterpret_cast<uint4*>(a0 + (2 * pw + 1) * 2048);
+      k2_gather_taps<BAND>(p, stg0, tile, 2 * pw, lane);
+      k2_gather_taps<BAND>(p, stg1, tile, 2 * pw + 1, lane);
+      k2_gather_blend(p, a0, stg0, 2 * pw, lane, []() {});
+      k2_gather_blend(p, a0, stg1, 2 * pw + 1, lane, []() {});
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[wg]);
+    }
+  }
+}
+
+template <bool ISSUER>
+__device__ __forceinline__ void k2_consumer_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
+  const int CH = cx.colhalf;
+  const uint32_t wsm = smem_u32(smem);
+  uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
+  float4* part = reinterpret_cast<float4*>(smem + k2Part) + cx.wg * 128;
+  const float* cs = reinterpret_cast<const float*>(smem + k2Const);
+  const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
+  const int ch0 = CH * 32;
+  const long tile_first = (long)blockIdx.x * 2 + cx.wg;
+  uint32_t round = 0;
+  for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2, ++round) {
+    if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
+    bool valid;
+    int jy_, jx_;
+    const long q = k2_query(p, tile, cx.row, valid, jy_, jx_);
+    SineTurn<9, 10> turn{cx.wg, tile == tile_first, tile + 1 < ntiles, tile - 1 + (long)gridDim.x * 2 < ntiles};
+    trace_mark(cx, 1);
+    if constexpr (ISSUER) {
+      // every accumulator slot was drained by the previous tile's last layer (its four step barriers); all the first
+      // layer's MMAs wait for is the producers' A tile
+      mbar_wait_or_trap(s.bars + 5 + cx.wg, round & 1);
+      cx.extra_commit = s.bars + 7 + cx.wg;
+    }
+    trace_mark(cx, 3);
+    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; }, [&](int, uint32_t(&v)[32], auto&& pf) {
+      if (STIF_K2_SINE_TURNS == 3) turn.template acquire<1>(0);
+      epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf);
+    });
+    cx.extra_commit = nullptr;
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if ((STIF_K2_SINE_TURNS == 1 || STIF_K2_SINE_TURNS == 2) && i == 0) turn.template acquire<STIF_K2_SINE_TURNS>(0);
+      epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
+      if (STIF_K2_SINE_TURNS == 2 && i == 3) turn.template release<2>(0);
+    });
+    float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    run_layer<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if (STIF_K2_SINE_TURNS == 2 && i == 0) turn.template acquire<2>(1);
+      epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf);
+      if (STIF_K2_SINE_TURNS && i == 3) turn.template release<(STIF_K2_SINE_TURNS == 2 ? 2 : 1)>(STIF_K2_SINE_TURNS == 2 ? 1 : 0);
+    });
+    if constexpr (ISSUER) continue;
+    const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
+    if (CH == 1) part[cx.row] = mine;
+    wg_barrier(cx.wg);
+    if (CH == 0 && valid) {
+      const float4 o = part[cx.row];
+      p.out[q] = mine.x + o.x + p.c.e4_b[0];
+      p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
+      p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
+    }
+  }
+}
+
+template <bool BAND>
+__global__ void __launch_bounds__(768, 1) k2_stage_cde_producer_kernel(const __grid_constant__ K2Params p) {
+  const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
+  {
+    float* cs = reinterpret_cast<float*>(smem + k2Const);
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) cs[kc2E4W + i] = p.c.e4_w[i];
+    __syncthreads();
+  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  mbar_wait_or_trap(&s.bars[0], 0);
+  if (warp >= 20) {
+    k2_producer_loop<BAND>(p, s, warp - 20, threadIdx.x & 31);
+  } else if (warp >= 4) {
+    WgCtx cx = make_wg<4>(s);
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
+    k2_consumer_loop<false>(p, s, cx);
+  } else if (warp < 2) {
+    WgCtx cx = make_wg<4>(s);
+    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
+    k2_consumer_loop<true>(p, s, cx);
+  }
+  cta_epilogue(s.tmem_base, 512);
+}
+
 void fill_from(float* dst, const std::vector<float>& src, size_t n) { std::copy(src.begin(), src.begin() + n, dst); }
 
 }  // namespace
@@ -1274,6 +1406,8 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_producer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_producer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (getenv("STIF_DEBUG_ATTRS")) {
@@ -1424,9 +1558,15 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.trace = trace_buffer();
   if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
   const bool band = k1_row_begin > 0 || k1_row_end < geo.HH;   // stage A+B rows are incomplete: check every weighted tap
+#if STIF_K2_PRODUCER
+  if (cudaError_t e = band ? launch_pdl(k2_stage_cde_producer_kernel<true>, grid, 768, k2Smem, cx.stream, p)
+                           : launch_pdl(k2_stage_cde_producer_kernel<false>, grid, 768, k2Smem, cx.stream, p))
+    return e;
+#else
   if (cudaError_t e = band ? launch_pdl(k2_stage_cde_kernel<true>, grid, 576, k2Smem, cx.stream, p)
                            : launch_pdl(k2_stage_cde_kernel<false>, grid, 576, k2Smem, cx.stream, p))
     return e;
+#endif
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
   return cudaGetLastError();

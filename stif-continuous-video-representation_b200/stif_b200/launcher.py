@@ -70,11 +70,11 @@ class QueryShardLauncher:
 
     def __init__(self, decode_fn: DecodeFn | None = None, group=None, device: torch.device | str | None = None,
                  mode: str = "bf16"):
-        if not dist.is_initialized():
-            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        # one process without a process group is the 1-GPU case of the same job (broadcasts become copies)
+        self.solo = not dist.is_initialized()
         self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
+        self.rank = 0 if self.solo else dist.get_rank(group)
+        self.world = 1 if self.solo else dist.get_world_size(group)
         self.device = torch.device(device) if device is not None else (
             torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
         self._decoder = None
@@ -89,7 +89,8 @@ class QueryShardLauncher:
             buf = t.to(self.device, torch.float32).contiguous()
         else:
             buf = torch.empty(shape, dtype=torch.float32, device=self.device)
-        dist.broadcast(buf, src, group=self.group)
+        if not self.solo:
+            dist.broadcast(buf, src, group=self.group)
         return buf
 
     def broadcast_weights(self, state_dict: dict | None, src: int = 0) -> dict:
@@ -147,13 +148,30 @@ class QueryShardLauncher:
 
     def decode(self, times: Sequence[float], out_size: tuple[int, int], halo: int = 32):
         """Decode this rank's share.  Returns ``[(WorkUnit, tensor[3,HH,WW])]``; for band units only rows
-        ``[row_begin,row_end)`` of the tensor are meaningful."""
+        ``[row_begin,row_end)`` of the tensor are meaningful.
+
+        All whole-slab units of one frame pair go through ONE decoder call (``times`` = this rank's timesteps of the
+        pair), so the t-independent latent projection runs once per pair and rank -- the reference repeats the
+        t-independent gathers in every iteration of its timestep loop (``Sakuya_arch_test.py:380-393``)."""
         if self.latent is None:
             raise RuntimeError("broadcast_inputs() first")
         P = self.latent.shape[0]
-        units = plan_units(P, len(times), out_size[0], self.world)
-        return [(u, self._decode_unit(u, float(times[u.t_index]), tuple(out_size), halo))
-                for u in units_for_rank(units, self.rank)]
+        HH = out_size[0]
+        mine = units_for_rank(plan_units(P, len(times), HH, self.world), self.rank)
+        results: dict[tuple, torch.Tensor] = {}
+        if self._decode_fn is None:
+            for pair in sorted({u.pair for u in mine}):
+                slabs = [u for u in mine if u.pair == pair and u.row_begin == 0 and u.row_end == HH]
+                if not slabs:
+                    continue
+                out = self._decoder.decode_stacked(self.latent[pair:pair + 1], self.frames[pair:pair + 1],
+                                                   [float(times[u.t_index]) for u in slabs], tuple(out_size))
+                for i, u in enumerate(slabs):
+                    results[(u.pair, u.t_index, u.row_begin)] = out[i, 0]
+        for u in mine:
+            if (u.pair, u.t_index, u.row_begin) not in results:
+                results[(u.pair, u.t_index, u.row_begin)] = self._decode_unit(u, float(times[u.t_index]), tuple(out_size), halo)
+        return [(u, results[(u.pair, u.t_index, u.row_begin)]) for u in mine]
 
     # ------------------------------------------------------------------ optional result collection
     def gather(self, results, times, out_size, dst: int = 0) -> torch.Tensor | None:
