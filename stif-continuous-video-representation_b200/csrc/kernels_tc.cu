@@ -63,6 +63,9 @@ constexpr uint32_t k1Part = k1WBytes, k1Const = k1Part + 2 * 128 * 16, k1Bars = 
 constexpr uint32_t k2E1 = 0, k2E2 = k2E1 + kW64x64, k2E3 = k2E2 + kW256x64, k2WBytes = k2E3 + kW256x256;
 constexpr uint32_t k2A0 = k2WBytes, k2Part = k2A0 + 2 * 16384, k2Const = k2Part + 2 * 128 * 16, k2Bars = k2Const + kc2Floats * 4,
                    k2Smem = k2Bars + 128;
+// K2, three-workgroup rotation: the same with three A tiles and three partial-sum exchanges
+constexpr uint32_t k2rPart = k2A0 + 3 * 16384, k2rConst = k2rPart + 3 * 128 * 16, k2rBars = k2rConst + kc2Floats * 4, k2rSmem = k2rBars + 128;
+static_assert(k2rSmem <= 232448, "exceeds 227 KB of shared memory");
 // K0: A tile (4 K-blocks x 128 rows) | W_tab (4 K-blocks x 256 rows)
 constexpr uint32_t k0A = 0, k0B = 4 * 128 * 128, k0WBytes = 4 * 256 * 128, k0Bars = k0B + k0WBytes, k0Smem = k0Bars + 128;
 static_assert(k2A0 % 1024 == 0 && k1F3 % 1024 == 0 && k1L1 % 1024 == 0 && k2E3 % 1024 == 0 && k0B % 1024 == 0,
@@ -129,9 +132,10 @@ struct WgCtx {
   uint64_t* full;      // two mbarriers: accumulator slot s is complete
   uint32_t n_issued, n_waited, n_steps;
   int wg, tid_wg, warp_in_wg, row, colhalf;
+  int bar_base;        // first of the two alternating step-barrier ids of the TMEM slot this warp works on (1 + 2 * slot)
+  int quarter;         // TMEM lane quarter of this warp (warp id % 4)
   int slot;            // logical warp slot: 0..15 epilogue warps (WG0 then WG1), 16/17 the issuers (trace rows, per-warp smem)
   bool issuer;         // this warp only issues the WG's MMAs (warps 0, 1); the other 8 warps of the WG only run epilogues
-  uint64_t* extra_commit;   // issuer only: a second mbarrier the next chunk's tcgen05.commit also arrives on ("operand tile read")
   long long* trace;    // this thread's trace cursor (null unless tracing)
 };
 
@@ -156,7 +160,7 @@ __device__ __forceinline__ void trace_mark(WgCtx& cx, int tag) {
 __device__ __forceinline__ void wg_barrier(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 5) : "memory"); }
 template <bool ISSUER>
 __device__ __forceinline__ void step_done(WgCtx& cx) {
-  const int id = 1 + cx.wg * 2 + (int)(cx.n_steps & 1);
+  const int id = cx.bar_base + (int)(cx.n_steps & 1);
   if (ISSUER) asm volatile("bar.sync %0, 288;" ::"r"(id) : "memory");
   else asm volatile("bar.arrive %0, 288;" ::"r"(id) : "memory");
   ++cx.n_steps;
@@ -188,6 +192,9 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
 #ifndef STIF_GATHER_TURNS
 #define STIF_GATHER_TURNS 1
 #endif
+#ifndef STIF_GATHER_ORDER
+#define STIF_GATHER_ORDER 0
+#endif
 // Both sides are unconditional (no tile counts): WG0 has as many tiles as WG1 or one more, so every sync finds its
 // partner; the at most one unmatched arrival per barrier is the very last one and nobody waits behind it.
 // WG1, top of every tile: wait for WG0's signal, acknowledge it.
@@ -218,10 +225,10 @@ __device__ __forceinline__ void gather_turn_done(const WgCtx& cx, bool first_til
 // hand-back first), and nobody waits for an arrival that is never made: WG0 owns tile 2b + 2Gj, WG1 tile 2b + 1 + 2Gj of
 // round j, so WG1's rounds are a prefix of WG0's and "does my partner have this / the next round" is a tile-index test.
 #ifndef STIF_K1_SINE_TURNS
-#define STIF_K1_SINE_TURNS 0
+#define STIF_K1_SINE_TURNS 1
 #endif
-#ifndef STIF_K2_PRODUCER
-#define STIF_K2_PRODUCER 0
+#ifndef STIF_K2_ROT
+#define STIF_K2_ROT 1
 #endif
 #ifndef STIF_K2_SINE_TURNS
 #define STIF_K2_SINE_TURNS 0
@@ -288,7 +295,6 @@ __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t
         else umma_ts(d, a_base + 8 * j, bdesc, idesc, j > 0);
       }
       umma_commit(&cx.full[slot]);
-      if (cx.extra_commit) umma_commit(cx.extra_commit);
     }
     __syncwarp();
     trace_mark(cx, 41);
@@ -495,10 +501,9 @@ __device__ __forceinline__ void epi_flow_first_layer(uint32_t (&v)[32], uint32_t
 
 // ---- common prologue / epilogue of the kernels -----------------------------------------------------
 struct CtaSetup {
-  uint64_t* bars;  // [0] weights landed, [1,2] WG0 slots, [3,4] WG1 slots, [5,6] / [7,8] producer hand-shake (see cta_prologue)
+  uint64_t* bars;  // [0] weights landed, [1,2] accumulator ring of TMEM slot 0, [3,4] of slot 1, [5,6] slot free (rotation kernel)
   uint32_t tmem_base;
 };
-constexpr int kProducerWarps = 4, kProducerThreads = kProducerWarps * 32;
 
 // Programmatic dependent launch: every kernel lets its successor in the stream be scheduled at once (its CTAs take SMs
 // as ours retire and run their prologue -- barrier init, TMEM allocation, the weight image's TMA load -- early), and
@@ -517,10 +522,7 @@ __device__ __forceinline__ CtaSetup cta_prologue(uint32_t bars_off, uint32_t w_o
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i <= 4; ++i) mbar_init(&s.bars[i], 1);
-    // producer kernels: [5,6] "first-layer tile of WG0 / WG1 is complete" (every producer thread arrives),
-    //                   [7,8] "... has been read by its MMAs" (one tcgen05.commit arrives)
-    for (int i = 5; i <= 6; ++i) mbar_init(&s.bars[i], kProducerThreads);
-    for (int i = 7; i <= 8; ++i) mbar_init(&s.bars[i], 1);
+    for (int i = 5; i <= 6; ++i) mbar_init(&s.bars[i], 1);   // rotation kernel: "TMEM slot 0 / 1 is free again" (its issuer arrives)
     fence_mbar_init();
   }
   if (tid < 32) {
@@ -572,9 +574,10 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   cx.tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0) + (uint32_t)cx.wg * 256u;
   cx.lane_addr = cx.tmem + ((uint32_t)(quarter * 32) << 16);
   cx.full = s.bars + 1 + 2 * cx.wg;
+  cx.bar_base = 1 + 2 * cx.wg;
+  cx.quarter = quarter;
   cx.n_issued = cx.n_waited = cx.n_steps = 0;
   cx.trace = nullptr;
-  cx.extra_commit = nullptr;
   return cx;
 }
 
@@ -1067,6 +1070,24 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
   __syncwarp();
 }
 
+// 16-byte read-only load with an L1 eviction-priority hint (tuning knob of the K2 gather: 0 default, 1 evict_last,
+// 2 no_allocate, 3 evict_first)
+#ifndef STIF_QTAP_HINT
+#define STIF_QTAP_HINT 0
+#endif
+#ifndef STIF_TTAP_HINT
+#define STIF_TTAP_HINT 0
+#endif
+template <int HINT>
+__device__ __forceinline__ uint4 ldg128_hint(const uint4* p) {
+  uint4 v;
+  if (HINT == 1) asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (HINT == 2) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else if (HINT == 3) asm volatile("ld.global.nc.L1::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  else v = __ldg(p);
+  return v;
+}
+
 // phase 2 (loads + blend + sine -> A tile)
 template <class Sig>
 __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane, Sig&& loads_issued) {
@@ -1089,7 +1110,9 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
     w[0] = wq.x; w[1] = wq.y; w[2] = wq.z; w[3] = wq.w;
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      v[k] = (STIF_DIAG & (k < 4 ? 8 : 16)) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>((k < 4 ? qtab_b : tab_b) + off[k]) + sub);
+      v[k] = (STIF_DIAG & (k < 4 ? 8 : 16)) ? make_uint4(0, 0, 0, 0)
+                                             : (k < 4 ? ldg128_hint<STIF_QTAP_HINT>(reinterpret_cast<const uint4*>(qtab_b + off[k]) + sub)
+                                                      : ldg128_hint<STIF_TTAP_HINT>(reinterpret_cast<const uint4*>(tab_b + off[k]) + sub));
   };
   __half2 acc2[4];
   // packed fp16 FMAs (2 channels per instruction, fp16 accumulate: the emulator shows the RGB error is unchanged)
@@ -1103,6 +1126,55 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
       for (int e = 0; e < 4; ++e) acc2[e] = __hfma2(*reinterpret_cast<const __half2*>(&w4[e]), w2, acc2[e]);
     }
   };
+#if STIF_GATHER_ORDER == 1
+  // Position-major order: the four rows of the warp's 4 x 4 query patch at warp position 0, then the four rows at position
+  // 1.  Consecutive half-steps then read vertically adjacent tap rows (half of a half-step's Q-table lines were touched by
+  // the previous one), so the reuse distance in the 28 KB L1 halves compared with alternating the two positions per row.
+  // Costs 12 more registers: the partial sums of all four rows stay live until the second position has been added.
+  __half2 acc4[4][4];
+  auto blend4 = [&](const uint4 (&v)[8], const uint32_t (&w)[4], __half2 (&acc)[4]) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __half2 wpair = *reinterpret_cast<const __half2*>(&w[k >> 1]);
+      const __half2 w2 = (k & 1) ? __high2half2(wpair) : __low2half2(wpair);
+      const uint32_t w4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = __hfma2(*reinterpret_cast<const __half2*>(&w4[e]), w2, acc[e]);
+    }
+  };
+  auto step_of = [](int i) { return ((i & 3) << 1) | (i >> 2); };   // i-th half-step in issue order -> (row = i & 3, position = i >> 2)
+  load_step(step_of(0), va, wa);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i + 1 < 8) {
+      if (i & 1) load_step(step_of(i + 1), va, wa);
+      else load_step(step_of(i + 1), vb, wb);
+    }
+    if (i + 1 == STIF_TURN_EARLY) loads_issued();
+    if (i < 4) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc4[i][e] = __float2half2_rn(0.f);
+    }
+    if ((i & 1) == 0) blend4(va, wa, acc4[i & 3]);
+    else blend4(vb, wb, acc4[i & 3]);
+    if (i >= 4) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t a = *reinterpret_cast<const uint32_t*>(&acc4[i & 3][e]);
+        acc[2 * e] = add_f16((uint16_t)(a & 0xFFFF), cE[2 * e]);
+        acc[2 * e + 1] = add_f16((uint16_t)(a >> 16), cE[2 * e + 1]);
+      }
+      // rows of this patch row may only be overwritten once every tap slot staged in them has been read: slots of row
+      // group `it` live in tile rows [4 it, 4 it + 4), and the loads of the LAST position of group `it` were issued one
+      // iteration ago (i - 1 >= 4 reads group (i - 1) & 3 ... i reads group i & 3: all issued before this store)
+      const int r = warp_in_wg * 16 + (i & 3) * 4 + (lane >> 3);
+      *reinterpret_cast<uint4*>(a0 + sw128_offset(r, sub * 8)) =
+          make_uint4(pack_bf16x2(fast_sin(acc[0]), fast_sin(acc[1])), pack_bf16x2(fast_sin(acc[2]), fast_sin(acc[3])),
+                     pack_bf16x2(fast_sin(acc[4]), fast_sin(acc[5])), pack_bf16x2(fast_sin(acc[6]), fast_sin(acc[7])));
+    }
+  }
+#else
   load_step(0, va, wa);
 #pragma unroll
   for (int s_ = 0; s_ < 8; ++s_) {
@@ -1130,6 +1202,7 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
                      pack_bf16x2(fast_sin(acc[4]), fast_sin(acc[5])), pack_bf16x2(fast_sin(acc[6]), fast_sin(acc[7])));
     }
   }
+#endif
   __syncwarp();
 }
 
@@ -1220,116 +1293,112 @@ __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_const
 }
 
 
-// ---- K2 with producer warps (STIF_K2_PRODUCER) -------------------------------------------------------------------------
-// 768 threads: warps 0, 1 issue, 2, 3 idle, 4..19 = the two epilogue workgroups, 20..23 = PRODUCERS.  The producers own stage
-// C + D and the hoisted first layer: warp position, bilinear footprints, the 16 tap loads per query, blend, sine, and the
-// bf16 SW128 A tile of the first MMA -- for WG0's and WG1's tiles alternately, running up to a tile ahead of the epilogue
-// workgroups, whose critical path (MMA round trips + sines) no longer contains the gather: it was 36 % of it.
-// Hand-shake per workgroup: bars[5 + wg] "A tile complete" (all 128 producer threads arrive after fence.proxy.async;
-// the WG's issuer waits for it before the first layer's MMAs), bars[7 + wg] "A tile read" (tcgen05.commit of those MMAs;
-// the producers wait for it before they overwrite the tile -- one tile of slack per WG with a single buffer, because the
-// first layer is the first thing a tile does).
-template <bool BAND>
-__device__ __forceinline__ void k2_producer_loop(const K2Params& p, const CtaSetup& s, int pw, int lane) {
-  const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
-  uint64_t* a_full = s.bars + 5;
-  uint64_t* a_empty = s.bars + 7;
-  uint32_t round = 0;
-  for (long base = (long)blockIdx.x * 2; base < ntiles; base += (long)gridDim.x * 2, ++round) {
-#pragma unroll 1
-    for (int wg = 0; wg < 2; ++wg) {
-      const long tile = base + wg;
-      if (tile >= ntiles) break;
-      uint8_t* a0 = smem + k2A0 + wg * 16384;
-      if (round > 0) mbar_wait_or_trap(&a_empty[wg], (round - 1) & 1);
-      // this warp stands in for two of the eight gather warps of the 18-warp kernel: tile rows [32 pw, 32 pw + 32)
-      uint4* stg0 = reinterpret_cast<uint4*>(a0 + (2 * pw) * 2048);
-      uint4* stg1 = reinterpret_cast<uint4*>(a0 + (2 * pw + 1) * 2048);
-      k2_gather_taps<BAND>(p, stg0, tile, 2 * pw, lane);
-      k2_gather_taps<BAND>(p, stg1, tile, 2 * pw + 1, lane);
-      k2_gather_blend(p, a0, stg0, 2 * pw, lane, []() {});
-      k2_gather_blend(p, a0, stg1, 2 * pw + 1, lane, []() {});
-      fence_proxy_async_smem();
-      mbar_arrive(&a_full[wg]);
-    }
-  }
-}
 
-template <bool ISSUER>
-__device__ __forceinline__ void k2_consumer_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
+// ---- K2 as a three-workgroup rotation over two TMEM slots (STIF_K2_ROT) ---------------------------------------------
+// A tile's life has a phase that needs no tensor memory -- the gather (warp positions, 16 tap loads per query, blend, first
+// sine -> the bf16 A tile in SHARED memory; 36 % of a workgroup's time per tile, MUFU almost idle) -- and a phase that
+// does (the three hidden layers: MMA round trips and 512 of the 640 sines).  With two workgroups the MUFU pipe idles
+// whenever both are outside their sine epilogues, which at ~60 % non-sine time each is ~35 % of the time (ncu: XU 58 %).
+// TMEM (512 columns = two tiles) forbids a third tile in the MMA phase, but not a third workgroup in the GATHER phase:
+//   832 threads = 2 issuer warps (one per TMEM slot) + 3 workgroups x 8 warps.  Tile n of the CTA is gathered and decoded by
+//   workgroup n % 3 on TMEM slot n % 2; while two workgroups run their MMA phases on the two slots the third gathers its
+//   next tile, then takes over the slot that frees up first in the static order.
+// Hand-over of a slot: its issuer warp runs the slot's tiles in order and arrives on bars[5 + slot] after the last step
+// barrier of a tile (every epilogue warp has drained the slot and made its last arrival on the slot's named barriers);
+// the next tile's workgroup waits for that before its first arrival on the same named barriers.  Counters restart per
+// tile: 10 step barriers (even, so the id alternation restarts at 0) and 9 accumulator chunks per tile (the ring position
+// of tile k of a slot is 9 k).
+template <bool ISSUER, bool BAND>
+__device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx, int me) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
-  uint8_t* a0 = smem + k2A0 + cx.wg * 16384;
-  float4* part = reinterpret_cast<float4*>(smem + k2Part) + cx.wg * 128;
-  const float* cs = reinterpret_cast<const float*>(smem + k2Const);
+  const int lane = threadIdx.x & 31, warp_in_wg = cx.warp_in_wg;
+  const float* cs = reinterpret_cast<const float*>(smem + k2rConst);
   const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
+  const long stride = gridDim.x;
   const int ch0 = CH * 32;
-  const long tile_first = (long)blockIdx.x * 2 + cx.wg;
-  uint32_t round = 0;
-  for (long tile = tile_first; tile < ntiles; tile += (long)gridDim.x * 2, ++round) {
-    if (cx.trace && tile >= (long)gridDim.x * 2 * 16) cx.trace = nullptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, s.tmem_base, 0);
+  uint64_t* slot_free = s.bars + 5;
+  constexpr int kStep = ISSUER ? 2 : 3;   // an issuer serves every second tile (its slot), a workgroup every third
+  uint8_t* a0_mine = smem + k2A0 + me * 16384;                                    // (workgroups only)
+  uint4* stg = reinterpret_cast<uint4*>(a0_mine + warp_in_wg * 2048);
+  float4* part = reinterpret_cast<float4*>(smem + k2rPart) + me * 128;
+  if constexpr (!ISSUER) {
+    const long t0 = (long)blockIdx.x + (long)me * stride;
+    if (t0 < ntiles) k2_gather_taps<BAND>(p, stg, t0, warp_in_wg, lane);
+  }
+  for (long n = me;; n += kStep) {
+    const long tile = (long)blockIdx.x + n * stride;
+    if (tile >= ntiles) break;
+    const int wg = (int)(n % 3), slot = (int)(n & 1);
+    const uint32_t seq = (uint32_t)(n >> 1);   // this tile is the slot's seq-th
+    cx.tmem = tmem_base + (uint32_t)slot * 256u;
+    cx.lane_addr = cx.tmem + ((uint32_t)(cx.quarter * 32) << 16);
+    cx.full = s.bars + 1 + 2 * slot;
+    cx.bar_base = 1 + 2 * slot;
+    cx.n_steps = 0;
+    cx.n_issued = cx.n_waited = 9u * seq;
+    uint8_t* a0 = smem + k2A0 + wg * 16384;
     bool valid;
     int jy_, jx_;
     const long q = k2_query(p, tile, cx.row, valid, jy_, jx_);
-    SineTurn<9, 10> turn{cx.wg, tile == tile_first, tile + 1 < ntiles, tile - 1 + (long)gridDim.x * 2 < ntiles};
     trace_mark(cx, 1);
-    if constexpr (ISSUER) {
-      // every accumulator slot was drained by the previous tile's last layer (its four step barriers); all the first
-      // layer's MMAs wait for is the producers' A tile
-      mbar_wait_or_trap(s.bars + 5 + cx.wg, round & 1);
-      cx.extra_commit = s.bars + 7 + cx.wg;
+    if constexpr (!ISSUER) {
+      // ---- gather phase: no tensor memory, no named barrier of the slot                       (:424-456)
+      k2_gather_blend(p, a0, stg, warp_in_wg, lane, []() {});
+      fence_proxy_async_smem();
+      tc_fence_before();
+      trace_mark(cx, 2);
+      if (seq > 0) mbar_wait_or_trap(&slot_free[slot], (seq - 1) & 1);   // the slot's previous tile has left it
+      tc_fence_after();
     }
+    step_done<ISSUER>(cx);
     trace_mark(cx, 3);
-    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; }, [&](int, uint32_t(&v)[32], auto&& pf) {
-      if (STIF_K2_SINE_TURNS == 3) turn.template acquire<1>(0);
-      epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf);
-    });
-    cx.extra_commit = nullptr;
+    // ---- MMA phase on the slot: encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe   (:456-457)
+    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
+                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
     run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
-      if ((STIF_K2_SINE_TURNS == 1 || STIF_K2_SINE_TURNS == 2) && i == 0) turn.template acquire<STIF_K2_SINE_TURNS>(0);
       epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
-      if (STIF_K2_SINE_TURNS == 2 && i == 3) turn.template release<2>(0);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
-      if (STIF_K2_SINE_TURNS == 2 && i == 0) turn.template acquire<2>(1);
-      epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf);
-      if (STIF_K2_SINE_TURNS && i == 3) turn.template release<(STIF_K2_SINE_TURNS == 2 ? 2 : 1)>(STIF_K2_SINE_TURNS == 2 ? 1 : 0);
-    });
-    if constexpr (ISSUER) continue;
+    layer_begin<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
+    if constexpr (!ISSUER) {   // footprints of this workgroup's next tile, under the first 256->256 chunk's MMA time
+      const long tile_next = tile + 3 * stride;
+      if (tile_next < ntiles) k2_gather_taps<BAND>(p, stg, tile_next, warp_in_wg, lane);
+    }
+    layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
+                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf); });
+    if constexpr (ISSUER) {
+      if (lane == 0) mbar_arrive(&slot_free[slot]);   // after the tile's last step barrier: the slot and its barrier ids are free
+      __syncwarp();
+      continue;
+    }
     const float4 mine = make_float4(rgb[0].x + rgb[0].y, rgb[1].x + rgb[1].y, rgb[2].x + rgb[2].y, 0.f);
     if (CH == 1) part[cx.row] = mine;
-    wg_barrier(cx.wg);
+    asm volatile("bar.sync %0, 256;" ::"r"(5 + me) : "memory");
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
       p.out[q] = mine.x + o.x + p.c.e4_b[0];
       p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
       p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
     }
+    // (`part` is rewritten one whole tile later, after the workgroup has passed two of its own barriers)
   }
 }
 
 template <bool BAND>
-__global__ void __launch_bounds__(768, 1) k2_stage_cde_producer_kernel(const __grid_constant__ K2Params p) {
-  const CtaSetup s = cta_prologue(k2Bars, 0, p.wimg, k2WBytes, 512);
+__global__ void __launch_bounds__(832, 1) k2_stage_cde_rot_kernel(const __grid_constant__ K2Params p) {
+  const CtaSetup s = cta_prologue(k2rBars, 0, p.wimg, k2WBytes, 512);
   {
-    float* cs = reinterpret_cast<float*>(smem + k2Const);
+    float* cs = reinterpret_cast<float*>(smem + k2rConst);
     for (int i = threadIdx.x; i < 768; i += blockDim.x) cs[kc2E4W + i] = p.c.e4_w[i];
     __syncthreads();
   }
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  WgCtx cx = make_wg(s);   // warps 0, 1: issuers (cx.wg = TMEM slot); warps 2..25: workgroups 0..2
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (cx.issuer ? 24 + cx.wg : cx.slot) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
-  if (warp >= 20) {
-    k2_producer_loop<BAND>(p, s, warp - 20, threadIdx.x & 31);
-  } else if (warp >= 4) {
-    WgCtx cx = make_wg<4>(s);
-    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
-    k2_consumer_loop<false>(p, s, cx);
-  } else if (warp < 2) {
-    WgCtx cx = make_wg<4>(s);
-    if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + cx.slot * 4096;
-    k2_consumer_loop<true>(p, s, cx);
-  }
+  if (cx.issuer) k2_rot_loop<true, BAND>(p, s, cx, cx.wg);
+  else k2_rot_loop<false, BAND>(p, s, cx, cx.wg);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -1406,8 +1475,8 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_producer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_producer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (getenv("STIF_DEBUG_ATTRS")) {
@@ -1481,7 +1550,7 @@ long long* trace_buffer() {
   if (!init) {
     init = true;
     if (getenv("STIF_TRACE")) {
-      cudaMalloc(&buf, 18 * 4096 * sizeof(long long));
+      cudaMalloc(&buf, 26 * 4096 * sizeof(long long));
     }
   }
   return buf;
@@ -1490,11 +1559,11 @@ void trace_dump(const char* kernel, cudaStream_t stream) {
   long long* buf = trace_buffer();
   if (!buf) return;
   cudaStreamSynchronize(stream);
-  std::vector<long long> h(18 * 4096);
+  std::vector<long long> h(26 * 4096);
   cudaMemcpy(h.data(), buf, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
   FILE* f = fopen(getenv("STIF_TRACE"), "a");
   if (!f) return;
-  for (int w = 0; w < 18; ++w) {
+  for (int w = 0; w < 26; ++w) {
     fprintf(f, "%s warp %d:", kernel, w);
     for (int i = 0; i + 1 < 4096 && h[w * 4096 + i] != 0; i += 2) fprintf(f, " %lld:%lld", h[w * 4096 + i], h[w * 4096 + i + 1]);
     fprintf(f, "\n");
@@ -1525,7 +1594,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
     const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
     p.trace = trace_buffer();
-    if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
+    if (p.trace) cudaMemsetAsync(p.trace, 0, 26 * 4096 * sizeof(long long), cx.stream);
     if ((stage == 3 || stage == 4) && !ws.ftab) return cudaErrorInvalidValue;
     if (stage == 5 && !ws.utab) return cudaErrorInvalidValue;
     if (cudaError_t e = stage == 1   ? launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)
@@ -1556,11 +1625,12 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   const long ntiles = (long)p.tiles_x * ((row_end - row_begin + 7) / 8);
   const int grid = (int)std::min<long>(cx.num_sms, (ntiles + 1) / 2);
   p.trace = trace_buffer();
-  if (p.trace) cudaMemsetAsync(p.trace, 0, 18 * 4096 * sizeof(long long), cx.stream);
+  if (p.trace) cudaMemsetAsync(p.trace, 0, 26 * 4096 * sizeof(long long), cx.stream);
   const bool band = k1_row_begin > 0 || k1_row_end < geo.HH;   // stage A+B rows are incomplete: check every weighted tap
-#if STIF_K2_PRODUCER
-  if (cudaError_t e = band ? launch_pdl(k2_stage_cde_producer_kernel<true>, grid, 768, k2Smem, cx.stream, p)
-                           : launch_pdl(k2_stage_cde_producer_kernel<false>, grid, 768, k2Smem, cx.stream, p))
+#if STIF_K2_ROT
+  const int grid_rot = (int)std::min<long>(cx.num_sms, ntiles);
+  if (cudaError_t e = band ? launch_pdl(k2_stage_cde_rot_kernel<true>, grid_rot, 832, k2rSmem, cx.stream, p)
+                           : launch_pdl(k2_stage_cde_rot_kernel<false>, grid_rot, 832, k2rSmem, cx.stream, p))
     return e;
 #else
   if (cudaError_t e = band ? launch_pdl(k2_stage_cde_kernel<true>, grid, 576, k2Smem, cx.stream, p)
