@@ -178,6 +178,14 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
 #ifndef STIF_EARLY_RELEASE
 #define STIF_EARLY_RELEASE 1
 #endif
+// -DSTIF_CHECK_BOUNDS: every table index the gathers / stores of K1 and K2 form is range-checked on the device and a
+// violation traps (the launch fails, the C ABI returns STIF_ECUDA).  compute-sanitizer is closed on the GPU pool this was
+// developed on, so the parity suite is run once per round against a build with these checks instead (profiles/).
+#ifdef STIF_CHECK_BOUNDS
+#define STIF_BOUND(idx, n) do { if ((long)(idx) < 0 || (long)(idx) >= (long)(n)) __trap(); } while (0)
+#else
+#define STIF_BOUND(idx, n) do { } while (0)
+#endif
 // Diagnostic builds only (results are WRONG): bit 0 drops the Q-table stores, bit 1 the TA loads, bit 2 the stage-B (TB) loads,
 // bit 3 K2's Q-table tap loads, bit 4 K2's TE tap loads -- what each memory stream costs end to end (profiles/diag_streams.sh).
 #ifndef STIF_DIAG
@@ -259,11 +267,38 @@ struct SineTurn {
   }
 };
 
+// STIF_WAIT_MODE: 0 = plain try_wait loop; 1 = try_wait with a suspend-time hint (the warp sleeps in hardware instead of
+// re-issuing the probe: spinning warps were taking ~15 % of the rotation kernel's issue slots); 2 = nanosleep back-off.
+#ifndef STIF_WAIT_MODE
+#define STIF_WAIT_MODE 0
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the warp in hardware for a bounded time, so this loop turns only a few times per wait; the
   // iteration cap converts a lost arrival into a launch failure instead of a hung GPU.
+#if STIF_WAIT_MODE == 1
+  for (uint32_t it = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++it)
+    if (it > (1u << 20)) __trap();
+#elif STIF_WAIT_MODE == 2
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    __nanosleep(40);
+    if (it > (1u << 22)) __trap();
+  }
+#else
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
     if (it > (1u << 24)) __trap();
+#endif
 }
 
 __device__ __forceinline__ bool elect_one() {
@@ -717,6 +752,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       const float rely = g.y.rel[jy], relx = g.x.rel[jx];
       const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
       const uint4* ta = tab4 + (inb ? ((long)iy * g.W + ix) : 0) * 32 + CH * 4;
+      STIF_BOUND(jy, g.HH); STIF_BOUND(jx, g.WW); STIF_BOUND(qc, (long)g.HH * g.WW);
       uint32_t pk[16];
       U8x32 ta2;
 #pragma unroll
@@ -762,7 +798,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
       const Taps tp = make_taps_tables(g, jy, jx);
       uint16_t wq[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) wq[k] = __half_as_ushort(__float2half_rn(tp.w[k]));
+      for (int k = 0; k < 4; ++k) { wq[k] = __half_as_ushort(__float2half_rn(tp.w[k])); STIF_BOUND(tp.off[k], (long)g.H * g.W); }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
@@ -816,6 +852,7 @@ __device__ __forceinline__ void k1_tile_loop(const K1Params& p, const CtaSetup& 
     wg_barrier(cx.wg);
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
+      STIF_BOUND(q, (long)g.HH * g.WW);
       reinterpret_cast<float4*>(p.flow)[q] =
           make_float4(mine.x + o.x + p.c.l3_b[0], mine.y + o.y + p.c.l3_b[1], mine.z + o.z + p.c.l3_b[2], mine.w + o.w + p.c.l3_b[3]);
     }
@@ -1046,6 +1083,9 @@ __device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, lo
     warp_position(g, jy, jx, which ? fl.z : fl.x, which ? fl.w : fl.y, gy, gx);   // (warplayer.py:25-39)
     Taps hr = make_taps(gy, gx, g.HH, g.WW);
     Taps lr = make_taps(gy, gx, g.H, g.W);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { STIF_BOUND(hr.off[k], (long)g.HH * g.WW); STIF_BOUND(lr.off[k], (long)g.H * g.W); }
+    STIF_BOUND(q, (long)g.HH * g.WW);
     // Row-band launches: rows outside [band_lo, band_hi) of the Q table (and the LR rows behind them) may not be
     // written yet.  A tap that carries weight there is a halo violation (flagged; the host repeats the launch);
     // a zero-weight tap is redirected to data that certainly exists (the query's own pixel / texel 0), because
@@ -1267,6 +1307,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     wg_barrier(cx.wg);
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
+      STIF_BOUND(q, p.plane);
       p.out[q] = mine.x + o.x + p.c.e4_b[0];
       p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
       p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
@@ -1378,6 +1419,7 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     asm volatile("bar.sync %0, 256;" ::"r"(5 + me) : "memory");
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
+      STIF_BOUND(q, p.plane);
       p.out[q] = mine.x + o.x + p.c.e4_b[0];
       p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
       p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
