@@ -136,6 +136,7 @@ struct WgCtx {
   int quarter;         // TMEM lane quarter of this warp (warp id % 4)
   int slot;            // logical warp slot: 0..15 epilogue warps (WG0 then WG1), 16/17 the issuers (trace rows, per-warp smem)
   bool issuer;         // this warp only issues the WG's MMAs (warps 0, 1); the other 8 warps of the WG only run epilogues
+  uint64_t* extra_commit;   // issuer only: a second mbarrier every chunk's tcgen05.commit also arrives on while it is set
   long long* trace;    // this thread's trace cursor (null unless tracing)
 };
 
@@ -235,6 +236,9 @@ __device__ __forceinline__ void gather_turn_done(const WgCtx& cx, bool first_til
 #ifndef STIF_K1_SINE_TURNS
 #define STIF_K1_SINE_TURNS 1
 #endif
+#ifndef STIF_K1_ROT
+#define STIF_K1_ROT 1
+#endif
 #ifndef STIF_K2_ROT
 #define STIF_K2_ROT 1
 #endif
@@ -330,6 +334,7 @@ __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t
         else umma_ts(d, a_base + 8 * j, bdesc, idesc, j > 0);
       }
       umma_commit(&cx.full[slot]);
+      if (cx.extra_commit) umma_commit(cx.extra_commit);
     }
     __syncwarp();
     trace_mark(cx, 41);
@@ -536,7 +541,7 @@ __device__ __forceinline__ void epi_flow_first_layer(uint32_t (&v)[32], uint32_t
 
 // ---- common prologue / epilogue of the kernels -----------------------------------------------------
 struct CtaSetup {
-  uint64_t* bars;  // [0] weights landed, [1,2] accumulator ring of TMEM slot 0, [3,4] of slot 1, [5,6] slot free (rotation kernel)
+  uint64_t* bars;  // [0] weights landed, [1,2] accumulator ring of TMEM slot 0, [3,4] of slot 1, [5,6] slot free, [7,8] h2 read (rotation kernels)
   uint32_t tmem_base;
 };
 
@@ -557,7 +562,8 @@ __device__ __forceinline__ CtaSetup cta_prologue(uint32_t bars_off, uint32_t w_o
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int i = 0; i <= 4; ++i) mbar_init(&s.bars[i], 1);
-    for (int i = 5; i <= 6; ++i) mbar_init(&s.bars[i], 1);   // rotation kernel: "TMEM slot 0 / 1 is free again" (its issuer arrives)
+    for (int i = 5; i <= 6; ++i) mbar_init(&s.bars[i], 1);   // rotation kernels: "TMEM slot 0 / 1 is free again" (its issuer arrives)
+    for (int i = 7; i <= 8; ++i) mbar_init(&s.bars[i], 3);   // K1 rotation: "slot's composed layer has read h2" (3 tcgen05.commit)
     fence_mbar_init();
   }
   if (tid < 32) {
@@ -613,6 +619,7 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   cx.quarter = quarter;
   cx.n_issued = cx.n_waited = cx.n_steps = 0;
   cx.trace = nullptr;
+  cx.extra_commit = nullptr;
   return cx;
 }
 
@@ -911,6 +918,177 @@ __global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_consta
   mbar_wait_or_trap(&s.bars[0], 0);
   if (cx.issuer) k1_tile_loop<true>(p, s, cx);
   else k1_tile_loop<false>(p, s, cx);
+  cta_epilogue(s.tmem_base, 512);
+}
+
+
+// ---- K1 as a three-workgroup rotation over two TMEM slots (STIF_K1_ROT) -----------------------------------------------
+// Same idea as K2's rotation (k2_rot_loop): tile n of the CTA belongs to workgroup n % 3 and runs its MMA phase on TMEM
+// slot n % 2.  What K1 can do without its slot is the tile-opening first layer (index tables -> TA row -> 64 sines); its
+// result h0 is parked in TMEM columns [0, 32) of the TARGET slot while the slot's previous tile is still in its flow
+// layers: those columns (part of h2) are dead once the composed layer's MMAs have completed, which the slot's issuer
+// reports on bars[7 + slot] (three commits, one per chunk of that layer).  The stage-B gather stays inside the MMA phase
+// (its sum has to live somewhere until the composed layer's F chunk arrives: as fp16 pairs in 16 registers here, the
+// kernel runs at 72 registers per thread).  13 accumulator chunks and 14 step barriers per tile.
+constexpr uint32_t kColH0 = 0;
+constexpr uint32_t k1rPart = k1WBytes, k1rConst = k1rPart + 3 * 128 * 16, k1rBars = k1rConst + kc1Floats * 4, k1rSmem = k1rBars + 128;
+static_assert(k1rSmem <= 232448, "exceeds 227 KB of shared memory");
+
+template <bool ISSUER>
+__device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s, WgCtx& cx, int me) {
+  const int CH = cx.colhalf;
+  const uint32_t wsm = smem_u32(smem);
+  const Geometry& g = p.g;
+  const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
+  const long stride = gridDim.x;
+  const uint4* __restrict__ tab4 = reinterpret_cast<const uint4*>(p.tab);
+  float4* part = reinterpret_cast<float4*>(smem + k1rPart) + me * 128;
+  const float* cs = reinterpret_cast<const float*>(smem + k1rConst);
+  const int ch0 = CH * 32;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, s.tmem_base, 0);
+  uint64_t* slot_free = s.bars + 5;
+  uint64_t* h2_read = s.bars + 7;
+  constexpr int kStep = ISSUER ? 2 : 3;
+  for (long n = me;; n += kStep) {
+    const long tile = (long)blockIdx.x + n * stride;
+    if (tile >= ntiles) break;
+    const int slot = (int)(n & 1);
+    const uint32_t seq = (uint32_t)(n >> 1);
+    cx.tmem = tmem_base + (uint32_t)slot * 256u;
+    cx.lane_addr = cx.tmem + ((uint32_t)(cx.quarter * 32) << 16);
+    cx.full = s.bars + 1 + 2 * slot;
+    cx.bar_base = 1 + 2 * slot;
+    cx.n_steps = 0;
+    cx.n_issued = cx.n_waited = 13u * seq;
+    const long q = p.q_begin + tile * kTile + cx.row;
+    const bool valid = q < p.q_end;
+    const long qc = valid ? q : p.q_end - 1;
+    const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
+    trace_mark(cx, 1);
+    // ---- stage A, first layer (hoisted), WITHOUT the slot: h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
+    if constexpr (!ISSUER) {
+      const int iy = g.y.idx[jy], ix = g.x.idx[jx];
+      const float rely = g.y.rel[jy], relx = g.x.rel[jx];
+      const bool inb = (iy >= 0) & (iy < g.H) & (ix >= 0) & (ix < g.W);
+      const uint4* ta = tab4 + (inb ? ((long)iy * g.W + ix) : 0) * 32 + CH * 4;
+      STIF_BOUND(jy, g.HH); STIF_BOUND(jx, g.WW); STIF_BOUND(qc, (long)g.HH * g.WW);
+      uint32_t pk[16];
+      U8x32 ta2;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if ((j & 1) == 0) ta2 = ldg256(ta + j);
+        uint32_t w4[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w4[e] = inb ? ta2.r[(j & 1) * 4 + e] : 0u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = ch0 + j * 8 + e * 2;
+          const float b0 = fmaf(rely, p.c.a_rel[2 * c], fmaf(relx, p.c.a_rel[2 * c + 1], p.c.cA[c]));
+          const float b1 = fmaf(rely, p.c.a_rel[2 * c + 2], fmaf(relx, p.c.a_rel[2 * c + 3], p.c.cA[c + 1]));
+          pk[j * 4 + e] = pack_bf16x2(fast_sin(add_f16((uint16_t)(w4[e] & 0xFFFF), b0)), fast_sin(add_f16((uint16_t)(w4[e] >> 16), b1)));
+        }
+      }
+      trace_mark(cx, 2);
+      if (seq > 0) {
+        mbar_wait_or_trap(&h2_read[slot], (seq - 1) & 1);   // the slot's previous tile no longer reads columns [0, 96)
+        tc_fence_after();
+      }
+      tmem_st16(cx.lane_addr + kColH0 + CH * 16, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      if (seq > 0) mbar_wait_or_trap(&slot_free[slot], (seq - 1) & 1);   // ... and has left the slot and its named barriers
+    }
+    step_done<ISSUER>(cx);
+    trace_mark(cx, 3);
+
+    // ---- feat_imnet hidden layers (MMA phase on the slot from here on)
+    run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColH0, wsm + k1F1, 64, [](int) { return 0; },
+                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
+    });
+
+    // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F
+    auto f3_order = [](int i) { return i == 2 ? 0 : i + 1; };
+    if constexpr (ISSUER) cx.extra_commit = &h2_read[slot];
+    layer_begin<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order);
+    // ---- stage B gather: gB = bilinear(TB; query position) + cB + composed bias of F, kept as 32 fp16 values  (:410-418)
+    uint32_t gBh[16];
+    if constexpr (!ISSUER) {
+      const Taps tp = make_taps_tables(g, jy, jx);
+      uint16_t wq[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { wq[k] = __half_as_ushort(__float2half_rn(tp.w[k])); STIF_BOUND(tp.off[k], (long)g.H * g.W); }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float gB[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) gB[e] = p.c.cB[ch0 + 16 * j + e] + p.c.f3_b[ch0 + 16 * j + e];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const U8x32 v = ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            gB[2 * e] = fma_f16((uint16_t)(v.r[e] & 0xFFFF), wq[k], gB[2 * e]);
+            gB[2 * e + 1] = fma_f16((uint16_t)(v.r[e] >> 16), wq[k], gB[2 * e + 1]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gBh[8 * j + e] = pack_half2(gB[2 * e], gB[2 * e + 1]);
+      }
+    }
+    trace_mark(cx, 4);
+    layer_finish<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
+      if (i < 2) {
+        epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
+      } else {   // f0 = sin(F + gB) -> bf16 -> TMEM
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pk[j] = pack_bf16x2(fast_sin(add_f16((uint16_t)(gBh[j] & 0xFFFF), __uint_as_float(v[2 * j]))),
+                              fast_sin(add_f16((uint16_t)(gBh[j] >> 16), __uint_as_float(v[2 * j + 1]))));
+        pf();
+        tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
+        tmem_st_wait();
+      }
+    });
+    if constexpr (ISSUER) cx.extra_commit = nullptr;
+
+    // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
+    run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
+                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
+    float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
+                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
+    if constexpr (ISSUER) {
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&slot_free[slot]);
+      __syncwarp();
+      continue;
+    }
+    const float4 mine = make_float4(fl[0].x + fl[0].y, fl[1].x + fl[1].y, fl[2].x + fl[2].y, fl[3].x + fl[3].y);
+    if (CH == 1) part[cx.row] = mine;
+    asm volatile("bar.sync %0, 256;" ::"r"(5 + me) : "memory");
+    if (CH == 0 && valid) {
+      const float4 o = part[cx.row];
+      STIF_BOUND(q, (long)g.HH * g.WW);
+      reinterpret_cast<float4*>(p.flow)[q] =
+          make_float4(mine.x + o.x + p.c.l3_b[0], mine.y + o.y + p.c.l3_b[1], mine.z + o.z + p.c.l3_b[2], mine.w + o.w + p.c.l3_b[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(832, 1) k1_stage_ab_rot_kernel(const __grid_constant__ K1Params p) {
+  const CtaSetup s = cta_prologue(k1rBars, 0, p.wimg, k1WBytes, 512);
+  {
+    float* cs = reinterpret_cast<float*>(smem + k1rConst);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) cs[kc1L3W + i] = p.c.l3_w[i];
+    __syncthreads();
+  }
+  WgCtx cx = make_wg(s);
+  if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (cx.issuer ? 24 + cx.wg : cx.slot) * 4096;
+  mbar_wait_or_trap(&s.bars[0], 0);
+  if (cx.issuer) k1_rot_loop<true>(p, s, cx, cx.wg);
+  else k1_rot_loop<false>(p, s, cx, cx.wg);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -1517,6 +1695,7 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
@@ -1639,6 +1818,14 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     if (p.trace) cudaMemsetAsync(p.trace, 0, 26 * 4096 * sizeof(long long), cx.stream);
     if ((stage == 3 || stage == 4) && !ws.ftab) return cudaErrorInvalidValue;
     if (stage == 5 && !ws.utab) return cudaErrorInvalidValue;
+#if STIF_K1_ROT
+    if (stage == 1) {
+      if (cudaError_t e = launch_pdl(k1_stage_ab_rot_kernel, (int)std::min<long>(cx.num_sms, ntiles), 832, k1rSmem, cx.stream, p)) return e;
+      ++*cx.launch_counter;
+      trace_dump("K1", cx.stream);
+      return cudaGetLastError();
+    }
+#endif
     if (cudaError_t e = stage == 1   ? launch_pdl(k1_stage_ab_kernel, grid, 576, k1Smem, cx.stream, p)
                         : stage == 3 ? launch_pdl(k1_ensemble_kernel<1>, grid, 576, k1Smem, cx.stream, p)
                         : stage == 4 ? launch_pdl(k1_ensemble_kernel<2>, grid, 576, k1Smem, cx.stream, p)
