@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define STIF_ABI_VERSION 1
+#define STIF_ABI_VERSION 2
 
 /* status codes */
 #define STIF_OK        0
@@ -146,6 +146,17 @@ int stif_decode_host(stif_decoder_t* dec,
                      int B, int H, int W, int HH, int WW,
                      const float* times_host, int T, int mode,
                      void* out_rgb_host);
+
+/* stif_decode_host for callers that hold the latent in bf16 (uint16_t bit patterns, [B,3,64,H,W], round-to-nearest-even of
+ * the encoder's fp32 output): half the host->device bytes, which are what bounds this entry point (PCIe).  The tensor-core
+ * path rounds the latent to bf16 before its first MMA anyway, so the result is bit-identical to stif_decode_host on the
+ * fp32 latent the bf16 values were rounded from.  Plain STIF_MODE_BF16 decodes only (STIF_FLAG_OUT_U8 may be added);
+ * frames stay fp32 (3 % of the bytes). */
+int stif_decode_host_bf16(stif_decoder_t* dec,
+                          const uint16_t* latent_bf16_host, const float* frames_host,
+                          int B, int H, int W, int HH, int WW,
+                          const float* times_host, int T, int mode,
+                          void* out_rgb_host);
 
 /* ---- introspection used by the parity tests (same device functions as the decode path) ---- */
 

@@ -103,7 +103,8 @@ struct K2Params {
   const __half* tab;
   const __half* qtab;
   const float* flow;
-  float* out;          // [3, plane]
+  float* out;          // [3, plane] fp32 planar, or ...
+  uint8_t* out_u8;     // ... [plane, 3] uint8 HWC (STIF_FLAG_OUT_U8: custom_video_test.py:102's conversion in the output stage), else null
   long plane;
   const uint8_t* wimg;
   int row_begin, row_end;   // output rows this launch decodes
@@ -115,7 +116,8 @@ struct K2Params {
   long long* trace;
 };
 struct K0Params {
-  const float* latent;  // [192, HW]
+  const float* latent;  // [192, HW] fp32, or ...
+  const uint16_t* latent16;   // ... bf16 bit patterns (stif_decode_host_bf16: the projection rounds the latent to bf16 anyway), else null
   const float* frames;  // [6, HW]
   __half* tab;          // [HW, 256]
   const uint8_t* wimg;  // W_tab, bf16, [256 x 256 (K padded)] SW128 image
@@ -539,6 +541,120 @@ __device__ __forceinline__ void epi_flow_first_layer(uint32_t (&v)[32], uint32_t
   tmem_st_wait();
 }
 
+
+// ---- half-chunk pipelined epilogues (rotation kernels) -----------------------------------------------------------------
+// A thread's 32 accumulator columns are fetched and processed as two 16-column halves A | B: while the sines of A run,
+// tcgen05.ld of B is in flight; while the sines of B run, the NEXT chunk's A half is in flight and A's tcgen05.st drains.
+// A workgroup that has the MUFU pipe to itself (the other one waiting for MMAs, gathering or storing) then loses ~80
+// instead of ~300 clocks per chunk to TMEM round trips.  Each tcgen05.wait::ld has exactly one load outstanding.
+//   epi(i, h, v16): process columns [16 h, 16 h + 16) of this thread's half of chunk i (v16 = the 16 accumulators).
+template <int NC, int KSTEPS, bool A_SMEM, bool ISSUER, class ChunkOf, class Epi>
+__device__ __forceinline__ void layer_finish2(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
+  if constexpr (ISSUER) {
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      step_done<true>(cx);
+      if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM, true>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));
+    }
+  } else {
+    uint32_t va[16], vb[16];
+    uint32_t addr = wait_chunk(cx);
+    tmem_ld16(addr, va);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      tmem_ld_wait();                       // A(i)
+      tmem_ld16(addr + 16, vb);             // B(i) in flight under A's sines
+      trace_mark(cx, 10 + i);
+      epi(i, 0, va);
+      tmem_ld_wait();                       // B(i): the accumulator slot is drained
+      const bool early = STIF_EARLY_RELEASE && i + 2 < NC;
+      if (early) {
+        tc_fence_before();
+        step_done<false>(cx);
+      }
+      if (i + 1 < NC) {                     // A(i + 1) in flight under B's sines
+        addr = wait_chunk(cx);
+        tmem_ld16(addr, va);
+      }
+      epi(i, 1, vb);
+      trace_mark(cx, 20 + i);
+      if (!early) {
+        tmem_st_wait();                     // covers every tcgen05.st of this layer so far (the next layer's A operand)
+        tc_fence_before();
+        step_done<false>(cx);
+      }
+      if (i + 2 < NC) issue_chunk<KSTEPS, A_SMEM, false>(cx, a_base, w_smem, n_rows, chunk_of(i + 2));   // (counter only)
+    }
+  }
+}
+template <int NC, int KSTEPS, bool A_SMEM, bool ISSUER, class ChunkOf, class Epi>
+__device__ __forceinline__ void run_layer2(WgCtx& cx, uint32_t a_base, uint32_t w_smem, int n_rows, ChunkOf chunk_of, Epi epi) {
+  layer_begin<NC, KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of);
+  layer_finish2<NC, KSTEPS, A_SMEM, ISSUER>(cx, a_base, w_smem, n_rows, chunk_of, epi);
+}
+
+// act = sin(acc + bias) -> bf16 -> 8 TMEM columns at dst (no wait: layer_finish2 waits once per late chunk)
+__device__ __forceinline__ void epi16_sin_to_tmem(const uint32_t (&v)[16], uint32_t dst, const float* __restrict__ bias) {
+  uint32_t pk[8];
+#ifdef STIF_DIAG_SKELETON   // diagnostic (WRONG results): the MMA / TMEM / barrier protocol alone
+#pragma unroll
+  for (int j = 0; j < 8; ++j) pk[j] = v[2 * j] & 0x3f803f80u;
+  tmem_st8(dst, pk);
+  return;
+#endif
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b4 = ldc4(bias + 4 * j4);
+    const float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
+    const float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
+    pk[2 * j4] = pack_bf16x2(fast_sin(a0.x), fast_sin(a0.y));
+    pk[2 * j4 + 1] = pack_bf16x2(fast_sin(a1.x), fast_sin(a1.y));
+  }
+  tmem_st8(dst, pk);
+}
+// act = sin(acc + bias) in fp32, contracted with the NOUT x 256 output layer on the FMA pipe
+template <int NOUT>
+__device__ __forceinline__ void epi16_sin_fma(const uint32_t (&v)[16], const float* __restrict__ bias, const float* __restrict__ w,
+                                              float2 (&acc)[NOUT]) {
+#ifdef STIF_DIAG_SKELETON
+  acc[0].x += __uint_as_float(v[0] & 0x3f800000u);
+  return;
+#endif
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b4 = ldc4(bias + 4 * j4);
+    float4 w4[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) w4[k] = ldc4(w + k * 256 + 4 * j4);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float2 s = add2(make_float2(__uint_as_float(v[4 * j4 + 2 * h]), __uint_as_float(v[4 * j4 + 2 * h + 1])),
+                      h ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
+      s.x = fast_sin(s.x);
+      s.y = fast_sin(s.y);
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) acc[k] = fma2(s, h ? make_float2(w4[k].z, w4[k].w) : make_float2(w4[k].x, w4[k].y), acc[k]);
+    }
+  }
+}
+// acc + bias -> fp16 -> 32 bytes of the projected HR table (one full sector)
+__device__ __forceinline__ void epi16_store_qtab(const uint32_t (&v)[16], const float* __restrict__ bias, __half* dst, bool valid) {
+  uint32_t o[8];
+#ifdef STIF_DIAG_SKELETON
+  if (v[0] == 0x12345678u) stg256(dst, v);
+  return;
+#endif
+#pragma unroll
+  for (int j4 = 0; j4 < 4; ++j4) {
+    const float4 b4 = ldc4(bias + 4 * j4);
+    const float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
+    const float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
+    o[2 * j4] = pack_half2(a0.x, a0.y);
+    o[2 * j4 + 1] = pack_half2(a1.x, a1.y);
+  }
+  if (valid) stg256(dst, o);
+}
+
 // ---- common prologue / epilogue of the kernels -----------------------------------------------------
 struct CtaSetup {
   uint64_t* bars;  // [0] weights landed, [1,2] accumulator ring of TMEM slot 0, [3,4] of slot 1, [5,6] slot free, [7,8] h2 read (rotation kernels)
@@ -644,7 +760,10 @@ __global__ void __launch_bounds__(512, 1) k0_project_kernel(const __grid_constan
 #pragma unroll
     for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[8 * i + e] = __ldg(p.latent + (long)((part + 4 * i) * 8 + e) * p.HW + m);
+      for (int e = 0; e < 8; ++e) {
+        const long at = (long)((part + 4 * i) * 8 + e) * p.HW + m;
+        v[8 * i + e] = p.latent16 ? __uint_as_float((uint32_t)__ldg(p.latent16 + at) << 16) : __ldg(p.latent + at);
+      }
     if (part == 0) {
 #pragma unroll
       for (int e = 0; e < 6; ++e) f[e] = __ldg(p.frames + (long)e * p.HW + m);
@@ -1002,10 +1121,11 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     trace_mark(cx, 3);
 
     // ---- feat_imnet hidden layers (MMA phase on the slot from here on)
-    run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColH0, wsm + k1F1, 64, [](int) { return 0; },
-                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.f1_b + ch0, pf); });
-    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
-      epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.f2_b + 64 * i + ch0, pf);
+    run_layer2<1, 4, false, ISSUER>(cx, cx.tmem + kColH0, wsm + k1F1, 64, [](int) { return 0; }, [&](int, int h, const uint32_t(&v)[16]) {
+      epi16_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.f1_b + ch0 + 16 * h);
+    });
+    run_layer2<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
+      epi16_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16 + h * 8, p.c.f2_b + 64 * i + ch0 + 16 * h);
     });
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F
@@ -1038,28 +1158,28 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
       }
     }
     trace_mark(cx, 4);
-    layer_finish<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, uint32_t(&v)[32], auto&& pf) {
+    layer_finish2<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, int h, const uint32_t(&v)[16]) {
       if (i < 2) {
-        epi_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0, p.qtab + qc * 128 + 64 * i + ch0, valid, pf);
+        epi16_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0 + 16 * h, p.qtab + qc * 128 + 64 * i + ch0 + 16 * h, valid);
       } else {   // f0 = sin(F + gB) -> bf16 -> TMEM
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          pk[j] = pack_bf16x2(fast_sin(add_f16((uint16_t)(gBh[j] & 0xFFFF), __uint_as_float(v[2 * j]))),
-                              fast_sin(add_f16((uint16_t)(gBh[j] >> 16), __uint_as_float(v[2 * j + 1]))));
-        pf();
-        tmem_st16(cx.lane_addr + kColAin + CH * 16, pk);
-        tmem_st_wait();
+        for (int j = 0; j < 8; ++j)
+          pk[j] = pack_bf16x2(fast_sin(add_f16((uint16_t)(gBh[8 * h + j] & 0xFFFF), __uint_as_float(v[2 * j]))),
+                              fast_sin(add_f16((uint16_t)(gBh[8 * h + j] >> 16), __uint_as_float(v[2 * j + 1]))));
+        tmem_st8(cx.lane_addr + kColAin + CH * 16 + h * 8, pk);
       }
     });
     if constexpr (ISSUER) cx.extra_commit = nullptr;
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
-    run_layer<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; },
-                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.l1_b + ch0, pf); });
+    run_layer2<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; }, [&](int, int h, const uint32_t(&v)[16]) {
+      epi16_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.l1_b + ch0 + 16 * h);
+    });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; },
-                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0, cs + kc1L3W + 64 * i + ch0, fl, pf); });
+    run_layer2<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
+      epi16_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0 + 16 * h, cs + kc1L3W + 64 * i + ch0 + 16 * h, fl);
+    });
     if constexpr (ISSUER) {
       if ((threadIdx.x & 31) == 0) mbar_arrive(&slot_free[slot]);
       __syncwarp();
@@ -1424,6 +1544,22 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
   __syncwarp();
 }
 
+// output stage: RGB of query q, either fp32 planar (the reference's tensor) or what its caller makes of it
+// (custom_video_test.py:102: `(img.clamp(0, 1) * 255).astype(uint8)` on the HWC frame -- fp32 clamp, fp32 multiply, truncation)
+__device__ __forceinline__ void k2_store_rgb(const K2Params& p, long q, float r, float g, float b) {
+  STIF_BOUND(q, p.plane);
+  if (p.out_u8) {
+    uint8_t* o = p.out_u8 + q * 3;
+    o[0] = (uint8_t)(fminf(fmaxf(r, 0.f), 1.f) * 255.f);
+    o[1] = (uint8_t)(fminf(fmaxf(g, 0.f), 1.f) * 255.f);
+    o[2] = (uint8_t)(fminf(fmaxf(b, 0.f), 1.f) * 255.f);
+  } else {
+    p.out[q] = r;
+    p.out[p.plane + q] = g;
+    p.out[2 * p.plane + q] = b;
+  }
+}
+
 template <bool ISSUER, bool BAND>
 __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx) {
   const int CH = cx.colhalf;
@@ -1485,10 +1621,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     wg_barrier(cx.wg);
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
-      STIF_BOUND(q, p.plane);
-      p.out[q] = mine.x + o.x + p.c.e4_b[0];
-      p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
-      p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
+      k2_store_rgb(p, q, mine.x + o.x + p.c.e4_b[0], mine.y + o.y + p.c.e4_b[1], mine.z + o.z + p.c.e4_b[2]);
     }
     // (`part` is rewritten one whole tile later; no warp can run that far ahead of a sibling: every chunk's MMA waits
     // for all eight warps' arrival on the step barrier)
@@ -1574,10 +1707,11 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     step_done<ISSUER>(cx);
     trace_mark(cx, 3);
     // ---- MMA phase on the slot: encode_imnet hidden layers; the 256->3 output layer rides the FMA pipe   (:456-457)
-    run_layer<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; },
-                 [&](int, uint32_t(&v)[32], auto&& pf) { epi_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16, p.c.e1_b + ch0, pf); });
-    run_layer<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, uint32_t(&v)[32], auto&& pf) {
-      epi_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16, p.c.e2_b + 64 * i + ch0, pf);
+    run_layer2<1, 4, true, ISSUER>(cx, smem_u32(a0), wsm + k2E1, 64, [](int) { return 0; }, [&](int, int h, const uint32_t(&v)[16]) {
+      epi16_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.e1_b + ch0 + 16 * h);
+    });
+    run_layer2<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k2E2, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
+      epi16_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16 + h * 8, p.c.e2_b + 64 * i + ch0 + 16 * h);
     });
     float2 rgb[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     layer_begin<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
@@ -1585,8 +1719,9 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
       const long tile_next = tile + 3 * stride;
       if (tile_next < ntiles) k2_gather_taps<BAND>(p, stg, tile_next, warp_in_wg, lane);
     }
-    layer_finish<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; },
-                 [&](int i, uint32_t(&v)[32], auto&& pf) { epi_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0, cs + kc2E4W + 64 * i + ch0, rgb, pf); });
+    layer_finish2<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
+      epi16_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0 + 16 * h, cs + kc2E4W + 64 * i + ch0 + 16 * h, rgb);
+    });
     if constexpr (ISSUER) {
       if (lane == 0) mbar_arrive(&slot_free[slot]);   // after the tile's last step barrier: the slot and its barrier ids are free
       __syncwarp();
@@ -1597,10 +1732,7 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     asm volatile("bar.sync %0, 256;" ::"r"(5 + me) : "memory");
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
-      STIF_BOUND(q, p.plane);
-      p.out[q] = mine.x + o.x + p.c.e4_b[0];
-      p.out[p.plane + q] = mine.y + o.y + p.c.e4_b[1];
-      p.out[2 * p.plane + q] = mine.z + o.z + p.c.e4_b[2];
+      k2_store_rgb(p, q, mine.x + o.x + p.c.e4_b[0], mine.y + o.y + p.c.e4_b[1], mine.z + o.z + p.c.e4_b[2]);
     }
     // (`part` is rewritten one whole tile later, after the workgroup has passed two of its own barriers)
   }
@@ -1748,9 +1880,10 @@ cudaError_t project_frames_up4_tc(const LaunchCtx& cx, const TcWeights* tw, cons
 }
 
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
-                              int W, void* tab, int row_begin, int row_end, bool test_variant) {
+                              int W, void* tab, int row_begin, int row_end, bool test_variant, bool latent_is_bf16) {
   K0Params p;
-  p.latent = latent192;
+  p.latent = latent_is_bf16 ? nullptr : latent192;
+  p.latent16 = latent_is_bf16 ? reinterpret_cast<const uint16_t*>(latent192) : nullptr;
   p.frames = frames6;
   p.tab = reinterpret_cast<__half*>(tab);
   p.wimg = test_variant ? tw->d_k0_lat : tw->d_k0;
@@ -1794,7 +1927,7 @@ void trace_dump(const char* kernel, cudaStream_t stream) {
 }  // namespace
 
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
-                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage) {
+                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage, uint8_t* out_u8) {
   const long WW = geo.WW;
   if (stage == 1 || stage == 3 || stage == 4 || stage == 5) {   // 1: fused stage A+B; 3 / 4: stage A / B of a local-ensemble pass; 5: fused, decoding_test at x4
     K1Params p;
@@ -1843,6 +1976,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.qtab = reinterpret_cast<const __half*>(ws.qtab);
   p.flow = ws.flow;
   p.out = out_rgb;
+  p.out_u8 = out_u8;
   p.plane = (long)geo.HH * geo.WW;
   p.wimg = tw->d_k2;
   p.row_begin = row_begin;

@@ -271,6 +271,7 @@ struct PipeGuard {
 // bands on `h2d` (K0 projects each band as soon as it lands) and every finished (t,b) slab is
 // downloaded on `d2h` while the next slab is being decoded.
 struct HostPipe {
+  int latent_elem;           // bytes per latent element on the host AND in the device staging copy: 4 (fp32) or 2 (bf16)
   const float* latent_host;
   const float* frames_host;
   void* out_host;            // fp32 [T,B,3,HH,WW], or uint8 [T,B,HH,WW,3] with STIF_FLAG_OUT_U8
@@ -332,15 +333,11 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
     if (g1 <= g0) return STIF_OK;
     for (int c = c0; c < c1; ++c) {
       ScopedSpan sp(d, stream, 2);
+      const size_t slab = ((size_t)c * B + b) * 3 * Q;
       cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, resident ? slab_ws(c) : ws, times[(size_t)c * B + b], g0, g1, 0, k1_hi,
-                                     out + ((size_t)c * B + b) * 3 * Q, 2);
+                                     out + slab, 2, hp.out_u8_dev ? hp.out_u8_dev + slab : nullptr);
       if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
     }
-    if (hp.out_u8_dev)
-      for (int c = c0; c < c1; ++c) {
-        const size_t slab = ((size_t)c * B + b) * 3 * Q;
-        CUDA_OR_RETURN(rgb_to_u8_hwc(cx, out + slab, hp.out_u8_dev + slab, HH, WW, g0, g1));
-      }
     CUDA_OR_RETURN(chain(stream, hp.d2h));
     for (int c = c0; c < c1; ++c) {
       const size_t slab = ((size_t)c * B + b) * 3 * Q, o = slab + (size_t)g0 * WW;
@@ -374,9 +371,10 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
       const int r0 = k ? lr_end[k - 1] : 0, r1 = lr_end[k];
       const size_t off = (size_t)b * 192 * plane + (size_t)r0 * W, offf = (size_t)b * 6 * plane + (size_t)r0 * W;
       const size_t width = (size_t)(r1 - r0) * W * sizeof(float);
+      const size_t le = (size_t)hp.latent_elem;
       if (r1 > r0) {
-        CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)latent + off, plane * 4, hp.latent_host + off, plane * 4, width, 192,
-                                         cudaMemcpyHostToDevice, hp.h2d));
+        CUDA_OR_RETURN(cudaMemcpy2DAsync((char*)latent + off * le, plane * le, (const char*)hp.latent_host + off * le, plane * le,
+                                         (size_t)(r1 - r0) * W * le, 192, cudaMemcpyHostToDevice, hp.h2d));
         CUDA_OR_RETURN(cudaMemcpy2DAsync((float*)frames + offf, plane * 4, hp.frames_host + offf, plane * 4, width, 6,
                                          cudaMemcpyHostToDevice, hp.h2d));
       }
@@ -386,14 +384,14 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
       landed[(size_t)b * nbands + k] = ev;
     }
   for (int b = 0; b < B; ++b) {
-    const float* lat_b = latent + (size_t)b * 192 * plane;
+    const float* lat_b = (const float*)((const char*)latent + (size_t)b * 192 * plane * hp.latent_elem);
     const float* fr_b = frames + (size_t)b * 6 * plane;
     for (int k = 0; k < nbands; ++k) {
       const int r0 = k ? lr_end[k - 1] : 0, r1 = lr_end[k];
       CUDA_OR_RETURN(cudaStreamWaitEvent(stream, landed[(size_t)b * nbands + k], 0));
       if (r1 > r0) {
         ScopedSpan sp(d, stream, 0);
-        CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1));
+        CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1, false, hp.latent_elem == 2));
       }
       mark(stream, "K0", b, k);
       const int h0 = k ? he[k - 1] : 0, h1 = he[k];
@@ -491,6 +489,8 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
     return set_error(STIF_ENOMEM, "workspace too small: %zu bytes given, %zu needed", workspace_bytes, need);
   CUDA_OR_RETURN(cudaSetDevice(d->device));
   if (hp && prec == STIF_MODE_BF16 && !ensemble && !test_variant) return decode_host_banded(d, latent, frames, B, H, W, HH, WW, times, T, mode, workspace, out, stream, *hp);
+  if (hp && hp->latent_elem != 4)
+    return set_error(STIF_EINVAL, "bf16 host latents (stif_decode_host_bf16) are supported by plain STIF_MODE_BF16 decodes only");
   const Geometry* geo = nullptr;
   if (int rc = get_geometry(d, H, W, HH, WW, stream, &geo, warp_from_coord)) return rc;
   Workspace ws = carve_workspace(workspace, H, W, HH, WW, mode);
@@ -542,15 +542,16 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
                             : decode_slab_tc_ensemble(cx, d->tcw, dg->geo_pass, dg->ens_y, dg->ens_x, ws, t, out_slab);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
+      const bool u8_fused = u8 && prec == STIF_MODE_BF16 && !ensemble;   // K2's output stage converts (no fp32 staging slab)
       for (int stage = 1; stage <= 2 && !ensemble; ++stage) {
         ScopedSpan sp(d, stream, stage);
         cudaError_t e = (prec == STIF_MODE_FP32)
                             ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
                             : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab,
-                                             stage == 1 && tc_variant ? 5 : stage);
+                                             stage == 1 && tc_variant ? 5 : stage, u8_fused ? out_u8 : nullptr);
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
-      if (u8) CUDA_OR_RETURN(rgb_to_u8_hwc(cx, ws.rgb32, out_u8, HH, WW, row_begin, row_end));
+      if (u8 && !u8_fused) CUDA_OR_RETURN(rgb_to_u8_hwc(cx, ws.rgb32, out_u8, HH, WW, row_begin, row_end));
       if (hp) {   // download this slab while the next one is decoded
         cudaEvent_t ev = take_event(d);
         used_events.push_back(ev);
@@ -696,8 +697,9 @@ int stif_decode_rows(stif_decoder_t* d, const float* latent, const float* frames
                      out, (cudaStream_t)stream, true);
 }
 
-int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* frames_host, int B, int H, int W, int HH,
-                     int WW, const float* times, int T, int mode, void* out_host) {
+namespace {
+int decode_host_entry(stif_decoder_t* d, const void* latent_host, int latent_elem, const float* frames_host, int B, int H, int W, int HH,
+                      int WW, const float* times, int T, int mode, void* out_host) {
   if (!d) return set_error(STIF_EINVAL, "null decoder");
   if (!latent_host || !frames_host || !out_host) return set_error(STIF_EINVAL, "null buffer");
   if (int rc = check_shape(B, H, W, HH, WW, T)) return rc;
@@ -707,7 +709,7 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
     CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->h2d_stream, cudaStreamNonBlocking));
     CUDA_OR_RETURN(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
   }
-  const size_t lat_b = align256((size_t)B * 192 * H * W * 4), fr_b = align256((size_t)B * 6 * H * W * 4);
+  const size_t lat_b = align256((size_t)B * 192 * H * W * latent_elem), fr_b = align256((size_t)B * 6 * H * W * 4);
   const size_t out_b = align256((size_t)T * B * 3 * HH * WW * 4);
   const size_t ws_b = stif_workspace_bytes(B, H, W, HH, WW, T, mode) + host_group_extra_bytes(HH, WW, T);
   const size_t out8_b = (mode & STIF_FLAG_OUT_U8) ? align256((size_t)T * B * 3 * HH * WW) : 0;
@@ -725,9 +727,22 @@ int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* f
   float* out = (float*)(base + lat_b + fr_b);
   void* ws = base + lat_b + fr_b + out_b;
   cudaStream_t s = d->host_stream;
-  HostPipe hp{latent_host, frames_host, out_host, out8_b ? (uint8_t*)base + lat_b + fr_b + out_b + ws_b : nullptr, d->h2d_stream, d->d2h_stream,
-              d->host_bands};
+  HostPipe hp{latent_elem, (const float*)latent_host, frames_host, out_host,
+              out8_b ? (uint8_t*)base + lat_b + fr_b + out_b + ws_b : nullptr, d->h2d_stream, d->d2h_stream, d->host_bands};
   return decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false, &hp);
+}
+}  // namespace
+
+int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* frames_host, int B, int H, int W, int HH,
+                     int WW, const float* times, int T, int mode, void* out_host) {
+  return decode_host_entry(d, latent_host, 4, frames_host, B, H, W, HH, WW, times, T, mode, out_host);
+}
+
+int stif_decode_host_bf16(stif_decoder_t* d, const uint16_t* latent_bf16_host, const float* frames_host, int B, int H, int W,
+                          int HH, int WW, const float* times, int T, int mode, void* out_host) {
+  if ((mode & 0xFF) != STIF_MODE_BF16 || (mode & (STIF_FLAG_LOCAL_ENSEMBLE | STIF_FLAG_TEST_VARIANT | STIF_FLAG_WARP_FROM_COORD)))
+    return set_error(STIF_EINVAL, "stif_decode_host_bf16: plain STIF_MODE_BF16 decodes only (STIF_FLAG_OUT_U8 allowed)");
+  return decode_host_entry(d, latent_bf16_host, 2, frames_host, B, H, W, HH, WW, times, T, mode, out_host);
 }
 
 int stif_debug_host_pipeline(stif_decoder_t* d, int bands, int halo, int64_t* respins) {

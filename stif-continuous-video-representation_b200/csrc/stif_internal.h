@@ -117,11 +117,15 @@ struct HostBandPlan {
 };
 HostBandPlan plan_host_bands(int H, int W, int HH, int WW, int G, int bands_hint, bool bands_forced, int halo, int num_sms);
 
+// out_u8 != null (stage 2 only): the slab's uint8 HWC frame is written by K2's output stage instead of fp32 planar RGB
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
-                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage);
+                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage,
+                           uint8_t* out_u8 = nullptr);
 cudaError_t project_frames_up4_tc(const LaunchCtx& cx, const TcWeights* tw, const float* frames6, int H, int W, void* utab);
+// latent_is_bf16: `latent192` points at bf16 bit patterns [192,H,W] instead of fp32 (host entry stif_decode_host_bf16)
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,
-                              int W, void* tab /* fp16 [H*W,256] */, int row_begin, int row_end, bool test_variant = false);
+                              int W, void* tab /* fp16 [H*W,256] */, int row_begin, int row_end, bool test_variant = false,
+                              bool latent_is_bf16 = false);
 int tc_selftest(int device, std::string& report);
 
 }  // namespace stif

@@ -241,10 +241,13 @@ class STIFQueryDecoder(torch.nn.Module):
     def decode_host(self, latent: np.ndarray | torch.Tensor, frames, times, scale=None, mode: str | None = None,
                     out: torch.Tensor | None = None, uint8: bool = False) -> torch.Tensor:
         """End-to-end call on HOST buffers (``stif_decode_host``): H2D copy, decode, D2H copy, sync.
-        ``uint8=True``: ``[T,B,HH,WW,3]`` uint8 frames as in ``decode_stacked`` (a quarter of the download)."""
+        ``uint8=True``: ``[T,B,HH,WW,3]`` uint8 frames as in ``decode_stacked`` (a quarter of the download).
+        A ``torch.bfloat16`` latent goes through ``stif_decode_host_bf16`` (half the upload; bit-identical to the call on
+        the fp32 latent it was rounded from, because the projection rounds to bf16 anyway)."""
         if not self._loaded:
             raise StifError("load_weights() has not been called")
-        lat = torch.as_tensor(latent, dtype=torch.float32).contiguous()
+        bf16_in = isinstance(latent, torch.Tensor) and latent.dtype == torch.bfloat16
+        lat = latent.contiguous() if bf16_in else torch.as_tensor(latent, dtype=torch.float32).contiguous()
         fr = torch.as_tensor(frames, dtype=torch.float32).contiguous()
         if lat.device.type != "cpu" or fr.device.type != "cpu":
             raise ValueError("decode_host takes host tensors")
@@ -258,8 +261,9 @@ class STIFQueryDecoder(torch.nn.Module):
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or out.device.type != "cpu":
             raise ValueError(f"out must be a contiguous host {dtype} {list(shape)} tensor")
         m = _MODES[mode or self.mode] | (STIF_FLAG_OUT_U8 if uint8 else 0)
-        check(lib.stif_decode_host(self._handle, lat.data_ptr(), fr.data_ptr(), B, H, W, HH, WW,
-                                   tm.ctypes.data_as(C.POINTER(C.c_float)), T, m, out.data_ptr()))
+        fn = lib.stif_decode_host_bf16 if bf16_in else lib.stif_decode_host
+        check(fn(self._handle, lat.data_ptr(), fr.data_ptr(), B, H, W, HH, WW,
+                 tm.ctypes.data_as(C.POINTER(C.c_float)), T, m, out.data_ptr()))
         return out
 
     # ------------------------------------------------------------------ north-star adapter

@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported(built_lib):
 def test_binding_lists_the_same_symbols(stif):
     from stif_b200 import _lib
     assert sorted(_lib.EXPORTS) == _declared_symbols()
-    assert _lib.lib.stif_abi_version() == 1
+    assert _lib.lib.stif_abi_version() == _lib.STIF_ABI_VERSION == 2
 
 
 def test_axis_tables_bit_exact_vs_torch_fixtures(stif):

@@ -607,3 +607,22 @@ def test_prepare_makes_decode_stream_ordered(stif):
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
     dec.close()
+
+
+def test_host_entry_bf16_latent_is_bit_identical(stif):
+    """stif_decode_host_bf16 on the RN-rounded latent == stif_decode_host on the fp32 latent it was rounded from (the
+    projection rounds to bf16 anyway), fp32 and uint8 outputs, banded pipeline included."""
+    lat, fr = synth.smooth_inputs(13, 1, 96, 128, 0.05)
+    dec = stif.STIFQueryDecoder(0, mode="bf16")
+    dec.load_weights(synth.make_weights(0, True))
+    dec.host_pipeline(bands=4)
+    lat32 = torch.from_numpy(lat)
+    lat16 = lat32.to(torch.bfloat16)
+    for u8 in (False, True):
+        a = dec.decode_host(lat32, fr, [0.25, 0.75], None, uint8=u8)
+        b = dec.decode_host(lat16, fr, [0.25, 0.75], None, uint8=u8)
+        assert torch.equal(a, b), u8
+    dev = dec.decode_stacked(lat32.cuda(), torch.from_numpy(fr).cuda(), [0.25, 0.75], None, uint8=True)
+    torch.cuda.synchronize()
+    assert torch.equal(dev.cpu(), b)                     # fused uint8 output stage == host pipeline's
+    dec.close()
