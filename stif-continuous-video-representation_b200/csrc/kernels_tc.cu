@@ -471,9 +471,13 @@ __device__ __forceinline__ void epi_sin_fma(uint32_t (&v)[32], const float* __re
   next_ld();
 }
 
+// two fp32 -> packed fp16x2, round-to-nearest-even, SATURATING to +-65504 (and NaN -> 0x7FFF stays NaN only for NaN
+// inputs): a projected-table entry beyond fp16's range -- first-layer pre-activations of ~6e4 rad, far outside anything a
+// SIREN produces -- must not become an Inf whose sine is a NaN for every query that gathers it
 __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
-  __half2 h = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 // acc + bias -> fp16 -> 64 bytes of the projected HR table
@@ -814,7 +818,10 @@ __global__ void __launch_bounds__(512, 1) k0_project_kernel(const __grid_constan
         tmem_ld32(src + c * 32, a);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = pack_half2(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+        // clamped to +-16000 rad: the sum of the four tables K2 blends in fp16 then stays finite whatever the latent holds
+        // (pre-activations of that size carry no information anyway: a bf16 operand's step there is 64 rad)
+        for (int j = 0; j < 16; ++j)
+          o[j] = pack_half2(fminf(fmaxf(__uint_as_float(a[2 * j]), -16000.f), 16000.f), fminf(fmaxf(__uint_as_float(a[2 * j + 1]), -16000.f), 16000.f));
         if (texel < p.m_end) {
           __half* dst = p.tab + texel * 256 + cq * 64 + c * 32;
           stg256(dst, o);
