@@ -54,11 +54,12 @@ extern "C" {
 #define STIF_FLAG_LOCAL_ENSEMBLE 0x100  /* decoding_localensemble semantics (Sakuya_arch_test.py:962-1085), either precision mode */
 #define STIF_FLAG_TEST_VARIANT   0x400  /* decoding_test semantics (Sakuya_arch_test.py:461-598, what VideoSRBaseModel.test runs):
                                          * the frame pair is bilinearly upsampled x4 (:513-514) before every bilinear frame
-                                         * gather.  STIF_MODE_FP32: any size.  STIF_MODE_BF16: the full x4 raster (HH = 4H, WW = 4W) only. */
+                                         * gather.  Both precision modes, any size (the tensor-core kernels have a fast path at the
+                                         * method's own x4, where the upsampled-frame grid is the query grid). */
 #define STIF_FLAG_WARP_FROM_COORD 0x800 /* warpgrid2 semantics (warplayer.py:41-47): the warp starts from the query's own
                                          * pixel-centre coordinate instead of the linspace base grid.  Together with
                                          * STIF_FLAG_TEST_VARIANT and stif_decode_rows this is decoding_memory
-                                         * (Sakuya_arch_test.py:600-861) without its file-system side effects.  FP32 only. */
+                                         * (Sakuya_arch_test.py:600-861) without its file-system side effects (stif_decode_window). */
 #define STIF_FLAG_OUT_U8         0x200  /* write what the reference's caller makes of the result (custom_video_test.py:102):
                                          * `(img.clamp(0,1).permute(1,2,0) * 255).astype(uint8)` -- uint8 [T,B,HH,WW,3],
                                          * fp32 clamp / multiply, truncation.  The `out` pointer is then a uint8_t buffer and
@@ -137,6 +138,18 @@ int stif_decode_rows(stif_decoder_t* dec,
                      int row_begin, int row_end, int halo,
                      void* workspace_dev, size_t workspace_bytes,
                      void* out_rgb_dev, void* stream);
+
+/* stif_decode_rows restricted further to columns [col_begin,col_end): the zoom window of decoding_memory
+ * (Sakuya_arch_test.py:600-861: stage A on the whole raster, stages B-E on a 4H x 4W window around `center`; use halo = HH,
+ * STIF_FLAG_TEST_VARIANT | STIF_FLAG_WARP_FROM_COORD).  Only the window is guaranteed to be written; the tensor-core kernels
+ * compute nothing else, the fp32 kernels decode the window's rows at full width. */
+int stif_decode_window(stif_decoder_t* dec,
+                       const float* latent_dev, const float* frames_dev,
+                       int B, int H, int W, int HH, int WW,
+                       const float* times_host, int T, int mode,
+                       int row_begin, int row_end, int col_begin, int col_end, int halo,
+                       void* workspace_dev, size_t workspace_bytes,
+                       void* out_rgb_dev, void* stream);
 
 /* End-to-end convenience for FFI callers that hold HOST buffers: allocates device memory
  * internally (cached on the handle), copies latent/frames host->device, decodes, copies RGB

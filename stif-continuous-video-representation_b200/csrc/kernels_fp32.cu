@@ -298,6 +298,84 @@ __global__ void project_frames_up4_kernel(const float* __restrict__ frames, int 
   utab[i] = s;
 }
 
+// ---- decoding_test on the tensor-core kernels at sizes other than x4 (Sakuya_arch_test.py:461-598) --------------------
+// utab [4H*4W, 192] fp16 = UB | UE1 | UE2, the frame terms of the three hoisted first layers on the x4-upsampled grid.
+// Thread = (query, 16-byte chunk of 8 channels); loads are 16 bytes, arithmetic fp32.
+__device__ __forceinline__ void blend8(const __half* __restrict__ row0, int chunk, const Taps& t, float (&acc)[8]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (t.w[k] == 0.f) continue;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(row0 + (long)t.off[k] * 192) + chunk);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h[e]);
+      acc[2 * e] = fmaf(t.w[k], f.x, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(t.w[k], f.y, acc[2 * e + 1]);
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&a)[8]) {
+  __half2 h[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(a[2 * e], a[2 * e + 1]);
+  return *reinterpret_cast<uint4*>(h);
+}
+// stage B's term (:520-523): uq[q, 0:64] = bilinear(UB; query position on the 4H x 4W grid); uq[q, 64:192] = 0 (the x4 kernel
+// that consumes this table folds columns 64..191 into the Q planes, which is only valid when the two grids coincide)
+__global__ void resample_ub_half_kernel(const __half* __restrict__ utab, Geometry g, __half* __restrict__ uq) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long Q = (long)g.HH * g.WW;
+  if (i >= Q * 24) return;
+  const long q = i / 24;
+  const int chunk = (int)(i - q * 24);
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (chunk < 8) {
+    const int jy = (int)(q / g.WW), jx = (int)(q - (long)jy * g.WW);
+    const Taps up = make_taps(query_coord(jy, g.HH), query_coord(jx, g.WW), 4 * g.H, 4 * g.W);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    blend8(utab, chunk, up, acc);
+    o = pack8(acc);
+  }
+  reinterpret_cast<uint4*>(uq + q * 192)[chunk] = o;
+}
+// stage D's terms (:548-551, :562-565): uadd[q] = bilinear(UE1; g1) + bilinear(UE2; g2) at the flow-warped positions
+__global__ void warp_u_terms_half_kernel(const __half* __restrict__ utab, const float* __restrict__ flow, Geometry g, long q_begin,
+                                         long q_end, __half* __restrict__ uadd) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long q = q_begin + (i >> 3);
+  if (q >= q_end) return;
+  const int chunk = (int)(i & 7);
+  const int jy = (int)(q / g.WW), jx = (int)(q - (long)jy * g.WW);
+  const float4 fl = __ldg(reinterpret_cast<const float4*>(flow) + q);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int wv = 0; wv < 2; ++wv) {
+    float gy, gx;
+    warp_position(g, jy, jx, wv == 0 ? fl.x : fl.z, wv == 0 ? fl.y : fl.w, gy, gx);
+    const Taps up = make_taps(gy, gx, 4 * g.H, 4 * g.W);
+    blend8(utab, 8 + 8 * wv + chunk, up, acc);
+  }
+  reinterpret_cast<uint4*>(uadd + q * 64)[chunk] = pack8(acc);
+}
+
+cudaError_t resample_ub_tc(const LaunchCtx& cx, const void* utab, const Geometry& geo, void* uq) {
+  const long n = (long)geo.HH * geo.WW * 24;
+  resample_ub_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx.stream>>>(reinterpret_cast<const __half*>(utab), geo,
+                                                                               reinterpret_cast<__half*>(uq));
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+cudaError_t warp_u_terms_tc(const LaunchCtx& cx, const void* utab, const float* flow, const Geometry& geo, int row_begin, int row_end,
+                            void* uadd) {
+  const long q0 = (long)row_begin * geo.WW, q1 = (long)row_end * geo.WW, n = (q1 - q0) * 8;
+  if (n <= 0) return cudaSuccess;
+  warp_u_terms_half_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx.stream>>>(reinterpret_cast<const __half*>(utab), flow, geo, q0, q1,
+                                                                                reinterpret_cast<__half*>(uadd));
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
 cudaError_t project_frames_up4(const LaunchCtx& cx, const DeviceWeights32& w, const float* frames6, int H, int W, float* utab) {
   const long n = (long)16 * H * W * 192;
   project_frames_up4_kernel<<<(unsigned)((n + 255) / 256), 256, 0, cx.stream>>>(frames6, H, W, w.w_up, utab);

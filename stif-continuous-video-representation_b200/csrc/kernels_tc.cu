@@ -108,6 +108,8 @@ struct K2Params {
   long plane;
   const uint8_t* wimg;
   int row_begin, row_end;   // output rows this launch decodes
+  int col_begin, col_end;   // ... and columns (the whole width except for decoding_memory's zoom window)
+  const __half* uadd;       // decoding_test away from x4: [HH*WW, 64] upsampled-frame terms at the warped positions (null otherwise)
   int tiles_x;              // K2 tiles are 8 rows x 16 columns (2 x 4 warp patches of 4 x 4 queries): neighbouring
                             // queries of a warp share bilinear taps in x AND y, so the L1 / in-flight-miss merge removes
                             // most of the duplicate line requests of the gather
@@ -203,9 +205,7 @@ __device__ __forceinline__ void step_done(WgCtx& cx) {
 #ifndef STIF_GATHER_TURNS
 #define STIF_GATHER_TURNS 1
 #endif
-#ifndef STIF_GATHER_ORDER
-#define STIF_GATHER_ORDER 0
-#endif
+
 // Both sides are unconditional (no tile counts): WG0 has as many tiles as WG1 or one more, so every sync finds its
 // partner; the at most one unmatched arrival per barrier is the very last one and nobody waits behind it.
 // WG1, top of every tile: wait for WG0's signal, acknowledge it.
@@ -1362,10 +1362,10 @@ __device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bo
   const int ty = t32 / p.tiles_x, tx = t32 - ty * p.tiles_x;
   const int patch = r >> 4, i = r & 15;
   const int y = p.row_begin + ty * 8 + (patch >> 2) * 4 + (i >> 2);
-  const int x = tx * 16 + (patch & 3) * 4 + (i & 3);
-  valid = (y < p.row_end) & (x < p.g.WW);
+  const int x = p.col_begin + tx * 16 + (patch & 3) * 4 + (i & 3);
+  valid = (y < p.row_end) & (x < p.col_end);
   jy = min(y, p.row_end - 1);
-  jx = min(x, p.g.WW - 1);
+  jx = min(x, p.col_end - 1);
   return (long)jy * p.g.WW + jx;
 }
 
@@ -1435,7 +1435,8 @@ __device__ __forceinline__ uint4 ldg128_hint(const uint4* p) {
 
 // phase 2 (loads + blend + sine -> A tile)
 template <class Sig>
-__device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane, Sig&& loads_issued) {
+__device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane, Sig&& loads_issued,
+                                                long tile = 0) {
   const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
   const char* __restrict__ tab_b = reinterpret_cast<const char*>(p.tab);
   const int sub = lane & 7;
@@ -1471,55 +1472,6 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
       for (int e = 0; e < 4; ++e) acc2[e] = __hfma2(*reinterpret_cast<const __half2*>(&w4[e]), w2, acc2[e]);
     }
   };
-#if STIF_GATHER_ORDER == 1
-  // Position-major order: the four rows of the warp's 4 x 4 query patch at warp position 0, then the four rows at position
-  // 1.  Consecutive half-steps then read vertically adjacent tap rows (half of a half-step's Q-table lines were touched by
-  // the previous one), so the reuse distance in the 28 KB L1 halves compared with alternating the two positions per row.
-  // Costs 12 more registers: the partial sums of all four rows stay live until the second position has been added.
-  __half2 acc4[4][4];
-  auto blend4 = [&](const uint4 (&v)[8], const uint32_t (&w)[4], __half2 (&acc)[4]) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const __half2 wpair = *reinterpret_cast<const __half2*>(&w[k >> 1]);
-      const __half2 w2 = (k & 1) ? __high2half2(wpair) : __low2half2(wpair);
-      const uint32_t w4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] = __hfma2(*reinterpret_cast<const __half2*>(&w4[e]), w2, acc[e]);
-    }
-  };
-  auto step_of = [](int i) { return ((i & 3) << 1) | (i >> 2); };   // i-th half-step in issue order -> (row = i & 3, position = i >> 2)
-  load_step(step_of(0), va, wa);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (i + 1 < 8) {
-      if (i & 1) load_step(step_of(i + 1), va, wa);
-      else load_step(step_of(i + 1), vb, wb);
-    }
-    if (i + 1 == STIF_TURN_EARLY) loads_issued();
-    if (i < 4) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc4[i][e] = __float2half2_rn(0.f);
-    }
-    if ((i & 1) == 0) blend4(va, wa, acc4[i & 3]);
-    else blend4(vb, wb, acc4[i & 3]);
-    if (i >= 4) {
-      float acc[8];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t a = *reinterpret_cast<const uint32_t*>(&acc4[i & 3][e]);
-        acc[2 * e] = add_f16((uint16_t)(a & 0xFFFF), cE[2 * e]);
-        acc[2 * e + 1] = add_f16((uint16_t)(a >> 16), cE[2 * e + 1]);
-      }
-      // rows of this patch row may only be overwritten once every tap slot staged in them has been read: slots of row
-      // group `it` live in tile rows [4 it, 4 it + 4), and the loads of the LAST position of group `it` were issued one
-      // iteration ago (i - 1 >= 4 reads group (i - 1) & 3 ... i reads group i & 3: all issued before this store)
-      const int r = warp_in_wg * 16 + (i & 3) * 4 + (lane >> 3);
-      *reinterpret_cast<uint4*>(a0 + sw128_offset(r, sub * 8)) =
-          make_uint4(pack_bf16x2(fast_sin(acc[0]), fast_sin(acc[1])), pack_bf16x2(fast_sin(acc[2]), fast_sin(acc[3])),
-                     pack_bf16x2(fast_sin(acc[4]), fast_sin(acc[5])), pack_bf16x2(fast_sin(acc[6]), fast_sin(acc[7])));
-    }
-  }
-#else
   load_step(0, va, wa);
 #pragma unroll
   for (int s_ = 0; s_ < 8; ++s_) {
@@ -1542,12 +1494,23 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
         acc[2 * e + 1] = add_f16((uint16_t)(a >> 16), cE[2 * e + 1]);
       }
       const int r = warp_in_wg * 16 + (s_ >> 1) * 4 + (lane >> 3);
+      if (p.uadd) {   // decoding_test away from x4: + bilinear(UE1; g1) + bilinear(UE2; g2), precomputed per query (warp_u_terms)
+        bool valid_;
+        int jy_, jx_;
+        const long q_ = k2_query(p, tile, r, valid_, jy_, jx_);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.uadd + q_ * 64) + sub);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] = add_f16((uint16_t)(uu[e] & 0xFFFF), acc[2 * e]);
+          acc[2 * e + 1] = add_f16((uint16_t)(uu[e] >> 16), acc[2 * e + 1]);
+        }
+      }
       *reinterpret_cast<uint4*>(a0 + sw128_offset(r, sub * 8)) =
           make_uint4(pack_bf16x2(fast_sin(acc[0]), fast_sin(acc[1])), pack_bf16x2(fast_sin(acc[2]), fast_sin(acc[3])),
                      pack_bf16x2(fast_sin(acc[4]), fast_sin(acc[5])), pack_bf16x2(fast_sin(acc[6]), fast_sin(acc[7])));
     }
   }
-#endif
   __syncwarp();
 }
 
@@ -1591,7 +1554,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
     trace_mark(cx, 1);
     if constexpr (!ISSUER) {
-      k2_gather_blend(p, a0, stg, warp_in_wg, lane, [&]() { gather_turn_done(cx, tile == tile_first); });
+      k2_gather_blend(p, a0, stg, warp_in_wg, lane, [&]() { gather_turn_done(cx, tile == tile_first); }, tile);
       fence_proxy_async_smem();
       tc_fence_before();
     }
@@ -1704,7 +1667,7 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     trace_mark(cx, 1);
     if constexpr (!ISSUER) {
       // ---- gather phase: no tensor memory, no named barrier of the slot                       (:424-456)
-      k2_gather_blend(p, a0, stg, warp_in_wg, lane, []() {});
+      k2_gather_blend(p, a0, stg, warp_in_wg, lane, []() {}, tile);
       fence_proxy_async_smem();
       tc_fence_before();
       trace_mark(cx, 2);
@@ -1934,7 +1897,8 @@ void trace_dump(const char* kernel, cudaStream_t stream) {
 }  // namespace
 
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
-                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage, uint8_t* out_u8) {
+                           int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage, uint8_t* out_u8,
+                           int col_begin, int col_end, const void* uadd) {
   const long WW = geo.WW;
   if (stage == 1 || stage == 3 || stage == 4 || stage == 5) {   // 1: fused stage A+B; 3 / 4: stage A / B of a local-ensemble pass; 5: fused, decoding_test at x4
     K1Params p;
@@ -1988,7 +1952,10 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   p.wimg = tw->d_k2;
   p.row_begin = row_begin;
   p.row_end = row_end;
-  p.tiles_x = (geo.WW + 15) / 16;
+  p.col_begin = col_begin < 0 ? 0 : col_begin;
+  p.col_end = col_end < 0 ? geo.WW : col_end;
+  p.uadd = reinterpret_cast<const __half*>(uadd);
+  p.tiles_x = (p.col_end - p.col_begin + 15) / 16;
   p.band_lo_off = k1_row_begin * geo.WW;
   p.band_hi_off = k1_row_end * geo.WW;
   p.flag = ws.flag;

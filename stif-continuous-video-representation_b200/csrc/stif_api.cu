@@ -117,7 +117,13 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
   ws.flow = (float*)take(Q * 4 * sizeof(float));
   ws.flag = (int*)take(256);
   if (mode & STIF_FLAG_OUT_U8) ws.rgb32 = (float*)take(Q * 3 * sizeof(float));
-  if (mode & STIF_FLAG_TEST_VARIANT) ws.utab = take((size_t)16 * H * W * 192 * esz);
+  if (mode & STIF_FLAG_TEST_VARIANT) {
+    ws.utab = take((size_t)16 * H * W * 192 * esz);
+    if (!fp32 && (HH != 4 * H || WW != 4 * W || (mode & STIF_FLAG_WARP_FROM_COORD))) {   // tensor-core path away from the x4 fast path
+      ws.uq = take(Q * 192 * 2);
+      ws.uadd = take(Q * 64 * 2);
+    }
+  }
   if (fp32) {
     ws.chunk = std::min<size_t>(Q, (size_t)1 << 18);
     ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
@@ -457,7 +463,8 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
 
 int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
                 const float* times, int T, int mode, int row_begin, int row_end, int halo, void* workspace,
-                size_t workspace_bytes, void* out_any, cudaStream_t stream, bool check_band, const HostPipe* hp = nullptr) {
+                size_t workspace_bytes, void* out_any, cudaStream_t stream, bool check_band, const HostPipe* hp = nullptr,
+                int col_begin = 0, int col_end = -1) {
   float* out = (float*)out_any;   // fp32 [T,B,3,HH,WW], or with STIF_FLAG_OUT_U8 uint8 [T,B,HH,WW,3] (see out_u8 below)
   if (!d) return set_error(STIF_EINVAL, "null decoder");
   if (!d->weights_loaded) return set_error(STIF_ESTATE, "stif_load_weights has not been called");
@@ -467,14 +474,20 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
   if (prec != STIF_MODE_BF16 && prec != STIF_MODE_FP32) return set_error(STIF_EINVAL, "unknown mode 0x%x", mode);
   const bool ensemble = (mode & STIF_FLAG_LOCAL_ENSEMBLE) != 0, u8 = (mode & STIF_FLAG_OUT_U8) != 0;
   const bool test_variant = (mode & STIF_FLAG_TEST_VARIANT) != 0, warp_from_coord = (mode & STIF_FLAG_WARP_FROM_COORD) != 0;
-  // tensor-core kernels: decoding_test only at x4, where the upsampled-frame grid IS the query grid (k1_tile_loop, UPF)
+  // tensor-core kernels, decoding_test: at x4 the upsampled-frame grid IS the query grid and the frame terms ride inside the Q
+  // planes (k1_tile_loop, UPF; "fast"); at any other size -- and for decoding_memory's coordinate warp base -- stage B's term is
+  // resampled onto the query grid once per pair and stage D's terms are gathered per slab at the warped positions (tc_general)
   const bool tc_variant = test_variant && prec == STIF_MODE_BF16;
+  const bool tc_general = tc_variant && (HH != 4 * H || WW != 4 * W || warp_from_coord);
+  if (col_end < 0) col_end = WW;
+  if (col_begin < 0 || col_end > WW || col_begin >= col_end)
+    return set_error(STIF_EINVAL, "invalid column window [%d,%d) for WW=%d", col_begin, col_end, WW);
   if ((test_variant || warp_from_coord) && ensemble)
     return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT / STIF_FLAG_WARP_FROM_COORD cannot be combined with STIF_FLAG_LOCAL_ENSEMBLE");
-  if (warp_from_coord && prec != STIF_MODE_FP32)
-    return set_error(STIF_EINVAL, "STIF_FLAG_WARP_FROM_COORD is available with STIF_MODE_FP32 only in this build");
-  if (tc_variant && (HH != 4 * H || WW != 4 * W || row_begin != 0 || row_end != HH))
-    return set_error(STIF_EINVAL, "STIF_FLAG_TEST_VARIANT with STIF_MODE_BF16 needs the full x4 raster (HH = 4H, WW = 4W); use STIF_MODE_FP32 otherwise");
+  if (warp_from_coord && prec == STIF_MODE_BF16 && !test_variant)
+    return set_error(STIF_EINVAL, "STIF_FLAG_WARP_FROM_COORD with STIF_MODE_BF16 needs STIF_FLAG_TEST_VARIANT (decoding_memory, Sakuya_arch_test.py:600-861)");
+  if ((col_begin != 0 || col_end != WW) && (ensemble || hp))
+    return set_error(STIF_EINVAL, "a column window needs device buffers and no STIF_FLAG_LOCAL_ENSEMBLE");
   if (ensemble && (B != 1 || row_begin != 0 || row_end != HH || hp))
     return set_error(STIF_EINVAL, "STIF_FLAG_LOCAL_ENSEMBLE needs B == 1 (Sakuya_arch_test.py:989) and a full raster on device buffers");
   // The tensor-core K2 gather stages tap addresses as 32-bit BYTE offsets (256 B per HR pixel, 512 B per LR texel,
@@ -522,7 +535,10 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
       ScopedSpan sp(d, stream, 0);
       if (prec == STIF_MODE_BF16) {
         CUDA_OR_RETURN(project_latent_tc(cx, d->tcw, lat_b, fr_b, H, W, ws.tab, r0, r1, tc_variant));
-        if (tc_variant && k == nbands - 1) CUDA_OR_RETURN(project_frames_up4_tc(cx, d->tcw, fr_b, H, W, ws.utab));
+        if (tc_variant && k == nbands - 1) {
+          CUDA_OR_RETURN(project_frames_up4_tc(cx, d->tcw, fr_b, H, W, ws.utab));
+          if (tc_general) CUDA_OR_RETURN(resample_ub_tc(cx, ws.utab, *geo, ws.uq));
+        }
       }
       else if (k == nbands - 1) {
         CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false, test_variant));
@@ -545,10 +561,19 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
       const bool u8_fused = u8 && prec == STIF_MODE_BF16 && !ensemble;   // K2's output stage converts (no fp32 staging slab)
       for (int stage = 1; stage <= 2 && !ensemble; ++stage) {
         ScopedSpan sp(d, stream, stage);
-        cudaError_t e = (prec == STIF_MODE_FP32)
-                            ? decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage)
-                            : decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab,
-                                             stage == 1 && tc_variant ? 5 : stage, u8_fused ? out_u8 : nullptr);
+        cudaError_t e;
+        if (prec == STIF_MODE_FP32) {
+          e = decode_slab_fp32(cx, d->w32, d->hw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, stage);
+        } else if (stage == 1) {
+          Workspace w1 = ws;
+          if (tc_general) w1.utab = ws.uq;   // the x4 kernel with "UB at the query | zeros": nothing is folded into the Q planes
+          e = decode_slab_tc(cx, d->tcw, *geo, w1, t, row_begin, row_end, k1_lo, k1_hi, out_slab, tc_variant ? 5 : 1);
+        } else {
+          e = tc_general ? warp_u_terms_tc(cx, ws.utab, ws.flow, *geo, row_begin, row_end, ws.uadd) : cudaSuccess;
+          if (e == cudaSuccess)
+            e = decode_slab_tc(cx, d->tcw, *geo, ws, t, row_begin, row_end, k1_lo, k1_hi, out_slab, 2, u8_fused ? out_u8 : nullptr,
+                               col_begin, col_end, tc_general ? ws.uadd : nullptr);
+        }
         if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
       }
       if (u8 && !u8_fused) CUDA_OR_RETURN(rgb_to_u8_hwc(cx, ws.rgb32, out_u8, HH, WW, row_begin, row_end));
@@ -732,6 +757,13 @@ int decode_host_entry(stif_decoder_t* d, const void* latent_host, int latent_ele
   return decode_impl(d, lat, fr, B, H, W, HH, WW, times, T, mode, 0, HH, 0, ws, ws_b, out, s, false, &hp);
 }
 }  // namespace
+
+int stif_decode_window(stif_decoder_t* d, const float* latent, const float* frames, int B, int H, int W, int HH, int WW,
+                       const float* times, int T, int mode, int row_begin, int row_end, int col_begin, int col_end, int halo,
+                       void* workspace, size_t workspace_bytes, void* out, void* stream) {
+  return decode_impl(d, latent, frames, B, H, W, HH, WW, times, T, mode, row_begin, row_end, halo, workspace, workspace_bytes,
+                     out, (cudaStream_t)stream, true, nullptr, col_begin, col_end);
+}
 
 int stif_decode_host(stif_decoder_t* d, const float* latent_host, const float* frames_host, int B, int H, int W, int HH,
                      int WW, const float* times, int T, int mode, void* out_host) {

@@ -77,6 +77,8 @@ struct Workspace {
   int* flag;      // device int: row-band halo violation flag
   void* utab;     // STIF_FLAG_TEST_VARIANT: [4H*4W,192] UB | UE1 | UE2 = frame columns applied to the x4-upsampled frames
                   // (fp32 in FP32 mode, fp16 in BF16 mode)
+  void* uq;       // STIF_FLAG_TEST_VARIANT, tensor-core path away from x4: [HH*WW,192] fp16 (UB at the query positions | zeros)
+  void* uadd;     // ... and [HH*WW,64] fp16 upsampled-frame terms of stage D for the slab being decoded
   float* rgb32;   // STIF_FLAG_OUT_U8: fp32 staging of one slab [3,HH*WW] ahead of the uint8 conversion
   size_t chunk;   // queries per activation chunk (FP32 mode)
   size_t total_bytes;
@@ -120,7 +122,13 @@ HostBandPlan plan_host_bands(int H, int W, int HH, int WW, int G, int bands_hint
 // out_u8 != null (stage 2 only): the slab's uint8 HWC frame is written by K2's output stage instead of fp32 planar RGB
 cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace& ws, float t,
                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* out_rgb, int stage,
-                           uint8_t* out_u8 = nullptr);
+                           uint8_t* out_u8 = nullptr, int col_begin = -1, int col_end = -1 /* stage 2: column window, default whole width */,
+                           const void* uadd = nullptr /* stage 2: [HH*WW,64] fp16 term added to the first layer (decoding_test away from x4) */);
+// decoding_test on the tensor-core kernels at sizes other than x4 (the upsampled-frame grid is then not the query grid):
+//   uq[HH*WW,192]  = UB bilinearly sampled at every query position | zeros  (per frame pair; k1_stage_ab_upf_kernel adds it)
+//   uadd[HH*WW,64] = bilinear(UE1; g1) + bilinear(UE2; g2) at the flow-warped positions of rows [row_begin,row_end) (per slab)
+cudaError_t resample_ub_tc(const LaunchCtx& cx, const void* utab, const Geometry& geo, void* uq);
+cudaError_t warp_u_terms_tc(const LaunchCtx& cx, const void* utab, const float* flow, const Geometry& geo, int row_begin, int row_end, void* uadd);
 cudaError_t project_frames_up4_tc(const LaunchCtx& cx, const TcWeights* tw, const float* frames6, int H, int W, void* utab);
 // latent_is_bf16: `latent192` points at bf16 bit patterns [192,H,W] instead of fp32 (host entry stif_decode_host_bf16)
 cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const float* latent192, const float* frames6, int H,

@@ -27,7 +27,7 @@ STIF_ABI_VERSION = 2
 # every symbol include/stif_b200.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
-    "stif_prepare", "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_host", "stif_decode_host_bf16", "stif_axis_tables",
+    "stif_prepare", "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_window", "stif_decode_host", "stif_decode_host_bf16", "stif_axis_tables",
     "stif_ensemble_weights", "stif_debug_last_flow", "stif_debug_host_pipeline", "stif_debug_band_plan", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
 ]
 
@@ -55,6 +55,8 @@ def _load():
                                 vp, C.c_size_t, vp, vp]
     lib.stif_decode_rows.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]
+    lib.stif_decode_window.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]
     lib.stif_decode_host.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, vp]
     lib.stif_decode_host_bf16.argtypes = lib.stif_decode_host.argtypes
     lib.stif_axis_tables.argtypes = [C.c_int, C.c_int, fp, ip, fp, fp]

@@ -150,7 +150,8 @@ class STIFQueryDecoder(torch.nn.Module):
     def decode_stacked(self, latent, frames, times, scale=None, mode: str | None = None,
                        rows: tuple[int, int] | None = None, halo: int = 0,
                        out: torch.Tensor | None = None, local_ensemble: bool = False, uint8: bool = False,
-                       test_variant: bool = False, warp_from_coord: bool = False) -> torch.Tensor:
+                       test_variant: bool = False, warp_from_coord: bool = False,
+                       cols: tuple[int, int] | None = None) -> torch.Tensor:
         """Decode to one ``[T,B,3,HH,WW]`` fp32 tensor.  ``rows=(r0,r1)`` restricts the call to a row band
         (``stif_decode_rows``), used by the sharding launcher.  ``uint8=True`` returns what the reference's caller
         saves (``custom_video_test.py:102``): ``(clamp(0,1) * 255).astype(uint8)`` as ``[T,B,HH,WW,3]``."""
@@ -171,7 +172,11 @@ class STIFQueryDecoder(torch.nn.Module):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         fp = tm.ctypes.data_as(C.POINTER(C.c_float))
         with torch.cuda.device(self.device):
-            if rows is None:
+            if rows is not None and cols is not None:
+                check(lib.stif_decode_window(self._handle, latent.data_ptr(), frames.data_ptr(), B, H, W, HH, WW, fp, T, m,
+                                             int(rows[0]), int(rows[1]), int(cols[0]), int(cols[1]), int(halo), ws.data_ptr(),
+                                             ws.numel(), out.data_ptr(), stream))
+            elif rows is None:
                 check(lib.stif_decode(self._handle, latent.data_ptr(), frames.data_ptr(), B, H, W, HH, WW, fp, T, m,
                                       ws.data_ptr(), ws.numel(), out.data_ptr(), stream))
             else:
@@ -189,13 +194,12 @@ class STIFQueryDecoder(torch.nn.Module):
         the bilinear frame gathers read the x4-upsampled frame pair.  ``scale`` is the reference's integer factor
         (``:467``) or, as the shipped evaluation loops pass it, an output size tuple.  At x4 (the default) the decoder's own
         mode is used -- on the tensor-core path the upsampled-frame terms share the query grid and ride inside the Q
-        table; any other size runs on the fp32 kernels."""
+        table; at any other size stage B's term is resampled onto the query grid once and stage D's terms are gathered
+        per timestep at the warped positions."""
         H, W = int(latent.shape[-2]), int(latent.shape[-1])
         if scale is not None and not isinstance(scale, (tuple, list)):
             scale = (H * int(scale), W * int(scale))
-        x4 = scale is None or (int(scale[0]), int(scale[1])) == (4 * H, 4 * W)
-        return list(self.decode_stacked(latent, frames, times, scale, mode=(mode or self.mode) if x4 else "fp32",
-                                        test_variant=True).unbind(0))
+        return list(self.decode_stacked(latent, frames, times, scale, mode=mode or self.mode, test_variant=True).unbind(0))
 
     @staticmethod
     def memory_window(H: int, W: int, HH: int, WW: int, center) -> tuple[int, int, int, int]:
@@ -215,19 +219,19 @@ class STIFQueryDecoder(torch.nn.Module):
             y0, y1 = y0 - (y1 - WW), WW
         return x0, x1, y0, y1
 
-    def decode_memory(self, latent, frames, times, scale, center) -> list[torch.Tensor]:
+    def decode_memory(self, latent, frames, times, scale, center, mode: str | None = None) -> list[torch.Tensor]:
         """``LunaTokis.decoding_memory`` (``Sakuya_arch_test.py:600-861``) WITHOUT its side effects (the hard-coded
         ``/home/users/...`` directories and JPEG saves, ``:609-651``): stage A on the whole ``scale = (HH, WW)`` raster,
         stages B-E -- ``decoding_test``'s upsampled frames, ``warpgrid2`` -- on the 4H x 4W window around ``center``.
-        Returns ``T`` tensors ``[B,3,4H,4W]``.  fp32 kernels; the window's rows are decoded as a row band over the full
-        width and the columns are cropped afterwards."""
+        Returns ``T`` tensors ``[B,3,4H,4W]``.  Decoded as a row + column window (``stif_decode_window``) in the decoder's
+        precision mode; the window is cropped out of the full-size output tensor."""
         H, W = int(latent.shape[-2]), int(latent.shape[-1])
         HH, WW = int(scale[0]), int(scale[1])
         if HH < 4 * H or WW < 4 * W:
             raise ValueError("decoding_memory needs an output raster at least as large as its 4H x 4W window")
         x0, x1, y0, y1 = self.memory_window(H, W, HH, WW, center)
-        full = self.decode_stacked(latent, frames, times, (HH, WW), mode="fp32", rows=(x0, x1), halo=HH, test_variant=True,
-                                   warp_from_coord=True)
+        full = self.decode_stacked(latent, frames, times, (HH, WW), mode=mode or self.mode, rows=(x0, x1), cols=(y0, y1), halo=HH,
+                                   test_variant=True, warp_from_coord=True)
         return list(full[:, :, :, x0:x1, y0:y1].contiguous().unbind(0))
 
     def decode_localensemble(self, latent, frames, times, scale=None, mode: str | None = None) -> torch.Tensor:
