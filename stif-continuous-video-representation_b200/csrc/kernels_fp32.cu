@@ -394,6 +394,14 @@ cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const 
 
 #define STIF_TRY(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) return e__; } while (0)
 
+// One dense layer C[M, N] = act(A[M, K] . W[n_off : n_off + N]^T + b): on the tensor cores (split-bf16, kernels_hp.cu)
+// when the handle carries the hi / lo weight images, else the SIMT SGEMM (STIF_FP32_SIMT=1: the test-only anchor).
+static cudaError_t dense_layer(const LaunchCtx& cx, const DeviceWeights32& w, int id, int n_off, int N, const float* A, int K,
+                               const float* Wt, const float* bias, float* C, long ldc, long M, int act) {
+  if (const HpLayer* L = hp_layer(w.hp, id)) return hp_gemm(cx, *L, n_off, N, A, bias + n_off, C, ldc, M, act);
+  return launch_gemm(cx, dense(A, K, Wt + (size_t)n_off * K, bias + n_off, C, ldc, M, N, act), false);
+}
+
 cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
                              const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
                              int k1_row_end, float* out_rgb, int stage) {
@@ -411,15 +419,15 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     stage_a_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, w.a_rel, cA, q0, n, ws.act_c);
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
-    STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 64, 1), false));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 64, 0), false));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
+    STIF_TRY(dense_layer(cx, w, HP_F1, 0, 64, ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 1));
+    STIF_TRY(dense_layer(cx, w, HP_F2, 0, 256, ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 1));
+    STIF_TRY(dense_layer(cx, w, HP_F3, 0, 64, ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 0));
+    STIF_TRY(dense_layer(cx, w, HP_F3, 64, 128, ws.act_b, 256, w.f3_w, w.f3_b, qtab + q0 * 128, 128, n, 0));
     stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr, reinterpret_cast<const float*>(ws.utab));
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
-    STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 256, 1), false));
+    STIF_TRY(dense_layer(cx, w, HP_L1, 0, 64, ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 1));
+    STIF_TRY(dense_layer(cx, w, HP_L2, 0, 256, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 1));
     STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, n, 4, 0), false));
   }
   // ---- K2: stage C + D + E over rows [row_begin, row_end)
@@ -430,9 +438,9 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
                                                       ws.flag, ws.act_c, reinterpret_cast<const float*>(ws.utab));
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
-    STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 64, 1), false));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.e2_w, w.e2_b, ws.act_b, 256, n, 256, 1), false));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.e3_w, w.e3_b, ws.act_a, 256, n, 256, 1), false));
+    STIF_TRY(dense_layer(cx, w, HP_E1, 0, 64, ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 1));
+    STIF_TRY(dense_layer(cx, w, HP_E2, 0, 256, ws.act_a, 64, w.e2_w, w.e2_b, ws.act_b, 256, n, 1));
+    STIF_TRY(dense_layer(cx, w, HP_E3, 0, 256, ws.act_b, 256, w.e3_w, w.e3_b, ws.act_a, 256, n, 1));
     GemmArgs g = dense(ws.act_a, 256, w.e4_w, w.e4_b, out_rgb + q0, 1, n, 3, 0);
     g.scm = 1; g.scn = Qall;  // planar [3,HH,WW] (Sakuya_arch_test.py:457)
     STIF_TRY(launch_gemm(cx, g, false));
@@ -466,10 +474,10 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
       stage_a_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, w.a_rel, cA, q0, n, ws.act_c);
       ++*cx.launch_counter;
       STIF_TRY(cudaGetLastError());
-      STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 64, 1), false));
-      STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 256, 1), false));
-      STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w, w.f3_b, ws.ftab + q0 * 64, 64, n, 64, 0), false));
-      STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.f3_w + 64 * 256, w.f3_b + 64, qtab + q0 * 128, 128, n, 128, 0), false));
+      STIF_TRY(dense_layer(cx, w, HP_F1, 0, 64, ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 1));
+      STIF_TRY(dense_layer(cx, w, HP_F2, 0, 256, ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 1));
+      STIF_TRY(dense_layer(cx, w, HP_F3, 0, 64, ws.act_b, 256, w.f3_w, w.f3_b, ws.ftab + q0 * 64, 64, n, 0));
+      STIF_TRY(dense_layer(cx, w, HP_F3, 64, 128, ws.act_b, 256, w.f3_w, w.f3_b, qtab + q0 * 128, 128, n, 0));
     }
     // stage B
     for (long q0 = 0; q0 < Q; q0 += chunk) {
@@ -478,8 +486,8 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
       stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, ws.ftab, nullptr);
       ++*cx.launch_counter;
       STIF_TRY(cudaGetLastError());
-      STIF_TRY(launch_gemm(cx, dense(ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 64, 1), false));
-      STIF_TRY(launch_gemm(cx, dense(ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 256, 1), false));
+      STIF_TRY(dense_layer(cx, w, HP_L1, 0, 64, ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 1));
+      STIF_TRY(dense_layer(cx, w, HP_L2, 0, 256, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 1));
       STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, n, 4, 0), false));
     }
     // stage C + D + E into the per-pass prediction, then the area-weighted accumulation

@@ -1,0 +1,258 @@
+// kernels_hp.cu -- the dense layers of the high-precision mode (STIF_MODE_FP32) on the tensor cores.
+//
+// STIF_MODE_FP32 evaluates the hoisted formulation layer by layer with fp32 activations in the workspace (kernels_fp32.cu).
+// Its GEMMs -- C[M,N] = act(A[M,K] W[N,K]^T + b), M = a chunk of queries, K in {64, 256}, N in {64, 128, 256} -- used to run
+// on a SIMT SGEMM.  Here they are tcgen05 MMAs on a 2-term bf16 split of BOTH operands,
+//     a = a_hi + a_lo,  w = w_hi + w_lo   (hi = bf16(x), lo = bf16(x - hi)),     a.w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo,
+// three MMAs per K step into the same fp32 TMEM accumulator (the dropped a_lo w_lo term is 2^-16 relative).  SURVEY.md
+// section 7.3-5 measured this split at 9e-6 max-abs RGB error with the stress weights, where single-pass TF32 gives 5.5e-4
+// and misses the 1e-4 bound.  Activations keep their accurate sinf; tables stay fp32.
+//
+// One CTA = 128 rows of A: the fp32 rows are read once (coalesced), split into hi / lo SW128 tiles in shared memory, and
+// reused for every 64-column chunk of N; the chunk's weight slices (hi and lo, pre-split and pre-swizzled on the host)
+// arrive by bulk TMA while the previous chunk's epilogue (bias, sinf, coalesced fp32 stores) runs from the other TMEM slot.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "stif_internal.h"
+#include "tc_pack.h"
+#include "tc_primitives.cuh"
+
+namespace stif {
+namespace {
+
+using namespace tc;
+
+struct HpGemmParams {
+  const float* A;          // [M, K] fp32, row stride K
+  const uint8_t* w_hi;     // SW128 image of the whole layer: K/64 K-blocks x n_total rows x 128 B (bf16 hi parts)
+  const uint8_t* w_lo;     // ... lo parts
+  const float* bias;       // [N] (already offset to the first output of this call), may be null
+  float* C;                // [M, ldc]
+  long ldc, M;
+  int n_total, n_off, N, K;
+  int act;                 // 0 identity, 1 sinf
+};
+
+extern __shared__ __align__(1024) uint8_t hp_smem[];
+
+__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > (1u << 24)) __trap();
+}
+
+template <int K>
+__global__ void __launch_bounds__(256, K == 64 ? 2 : 1) hp_gemm_kernel(const __grid_constant__ HpGemmParams p) {
+  constexpr int KB = K / 64;                                     // 64-wide K blocks
+  constexpr uint32_t kA = KB * 16384u, kW = KB * 8192u;          // bytes of one A tile (hi or lo) / one weight slice
+  uint8_t* sA_hi = hp_smem;
+  uint8_t* sA_lo = sA_hi + kA;
+  uint8_t* sW_hi = sA_lo + kA;
+  uint8_t* sW_lo = sW_hi + kW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW_lo + kW);      // [0] weights landed, [1] weights read, [2,3] accumulator slot ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long m0 = (long)blockIdx.x * 128;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  // ---- A tile: fp32 rows -> (hi, lo) bf16 SW128 tiles; 4 consecutive k per thread and step (one float4)
+  for (int idx = tid; idx < 128 * (K / 4); idx += 256) {
+    const int row = idx / (K / 4), k = (idx - row * (K / 4)) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m0 + row < p.M) v = __ldg(reinterpret_cast<const float4*>(p.A + (m0 + row) * K + k));
+    const uint32_t h0 = pack_bf16x2(v.x, v.y), h1 = pack_bf16x2(v.z, v.w);
+    const float r0 = v.x - __uint_as_float(h0 << 16), r1 = v.y - __uint_as_float(h0 & 0xFFFF0000u);
+    const float r2 = v.z - __uint_as_float(h1 << 16), r3 = v.w - __uint_as_float(h1 & 0xFFFF0000u);
+    const uint32_t off = (uint32_t)(k >> 6) * 16384u + sw128_offset(row, k & 63);
+    *reinterpret_cast<uint2*>(sA_hi + off) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(sA_lo + off) = make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int nchunks = p.N / 64;
+  const int quarter = warp & 3, colhalf = warp >> 2;
+  auto epilogue = [&](int c) {
+    wait_or_trap(&bars[2 + (c & 1)], (c >> 1) & 1);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c & 1) * 64u + (uint32_t)colhalf * 32u, v);
+    tmem_ld_wait();
+    const long row = m0 + quarter * 32 + lane;
+    const int col0 = c * 64 + colhalf * 32;
+    float o[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+      o[j] = p.act ? sinf(x) : x;
+    }
+    if (row < p.M) {
+      float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+    tc_fence_before();
+  };
+  for (int c = 0; c < nchunks; ++c) {
+    if (tid == 0) {
+      if (c > 0) wait_or_trap(&bars[1], (c - 1) & 1);            // the previous chunk's MMAs have read the weight slices
+      mbar_arrive_expect_tx(&bars[0], 2 * kW);
+      const size_t kb_stride = (size_t)p.n_total * 128, row_off = (size_t)(p.n_off + c * 64) * 128;
+      for (int kb = 0; kb < KB; ++kb) {
+        bulk_copy_g2s(sW_hi + kb * 8192, p.w_hi + kb * kb_stride + row_off, 8192, &bars[0]);
+        bulk_copy_g2s(sW_lo + kb * 8192, p.w_lo + kb * kb_stride + row_off, 8192, &bars[0]);
+      }
+      wait_or_trap(&bars[0], c & 1);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc_bf16(128, 64), d = tmem + (uint32_t)(c & 1) * 64u;
+      const uint32_t ah = smem_u32(sA_hi), al = smem_u32(sA_lo), wh = smem_u32(sW_hi), wl = smem_u32(sW_lo);
+      bool first = true;
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {                     // a_hi w_hi, a_lo w_hi, a_hi w_lo
+        const uint32_t a = term == 1 ? al : ah, w = term == 2 ? wl : wh;
+#pragma unroll
+        for (int j = 0; j < K / 16; ++j) {
+          umma_ss(d, make_desc_sw128(a + (j >> 2) * 16384) + 2 * (j & 3), make_desc_sw128(w + (j >> 2) * 8192) + 2 * (j & 3), idesc, !first);
+          first = false;
+        }
+      }
+      umma_commit(&bars[2 + (c & 1)]);
+      umma_commit(&bars[1]);
+    }
+    __syncwarp();
+    if (c > 0) epilogue(c - 1);                                  // overlaps this chunk's weight TMA + MMAs
+    __syncthreads();                                             // slot (c - 1) & 1 is drained before chunk c + 1 is issued into it
+  }
+  epilogue(nchunks - 1);
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+template <int K>
+constexpr size_t hp_smem_bytes() { return 2 * (size_t)(K / 64) * 16384 + 2 * (size_t)(K / 64) * 8192 + 64; }
+
+void split_images(const std::vector<float>& w, int N, int K, std::vector<uint8_t>& hi, std::vector<uint8_t>& lo) {
+  std::vector<float> h((size_t)N * K), l((size_t)N * K);
+  for (size_t i = 0; i < h.size(); ++i) {
+    h[i] = bf16_round_host(w[i]);
+    l[i] = w[i] - h[i];
+  }
+  append_sw128_image(hi, h.data(), N, K);
+  append_sw128_image(lo, l.data(), N, K);
+}
+
+}  // namespace
+
+struct HpWeights {
+  HpLayer layer[8];
+};
+
+const HpLayer* hp_layer(const HpWeights* w, int id) { return w ? &w->layer[id] : nullptr; }
+
+HpWeights* hp_weights_create(const FoldedWeights& hw, std::string& err) {
+  auto* t = new HpWeights();
+  const std::vector<float>* src[8] = {&hw.f1_w, &hw.f2_w, &hw.f3_w, &hw.l1_w, &hw.l2_w, &hw.e1_w, &hw.e2_w, &hw.e3_w};
+  const int N[8] = {64, 256, 192, 64, 256, 64, 256, 256}, K[8] = {64, 64, 256, 64, 64, 64, 64, 256};
+  for (int i = 0; i < 8; ++i) t->layer[i] = HpLayer{nullptr, nullptr, N[i], K[i]};
+  for (int i = 0; i < 8; ++i) {
+    std::vector<uint8_t> hi, lo;
+    split_images(*src[i], N[i], K[i], hi, lo);
+    cudaError_t e = cudaMalloc(&t->layer[i].hi, hi.size());
+    if (e == cudaSuccess) e = cudaMalloc(&t->layer[i].lo, lo.size());
+    if (e == cudaSuccess) e = cudaMemcpy(t->layer[i].hi, hi.data(), hi.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t->layer[i].lo, lo.data(), lo.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      err = cudaGetErrorString(e);
+      hp_weights_destroy(t);
+      return nullptr;
+    }
+  }
+  cudaError_t e = cudaFuncSetAttribute(hp_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<64>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<256>());
+  if (e != cudaSuccess) {
+    err = cudaGetErrorString(e);
+    hp_weights_destroy(t);
+    return nullptr;
+  }
+  return t;
+}
+
+void hp_weights_destroy(HpWeights* t) {
+  if (!t) return;
+  for (auto& l : t->layer) {
+    if (l.hi) cudaFree(l.hi);
+    if (l.lo) cudaFree(l.lo);
+  }
+  delete t;
+}
+
+cudaError_t hp_gemm(const LaunchCtx& cx, const HpLayer& L, int n_off, int N, const float* A, const float* bias, float* C, long ldc,
+                    long M, int act) {
+  if (M <= 0) return cudaSuccess;
+  if (N % 64 != 0 || n_off % 8 != 0 || n_off + N > L.N || (L.K != 64 && L.K != 256) || ldc % 4 != 0) return cudaErrorInvalidValue;
+  HpGemmParams p{A, L.hi, L.lo, bias, C, ldc, M, L.N, n_off, N, L.K, act};
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  if (L.K == 64) hp_gemm_kernel<64><<<grid, 256, hp_smem_bytes<64>(), cx.stream>>>(p);
+  else hp_gemm_kernel<256><<<grid, 256, hp_smem_bytes<256>(), cx.stream>>>(p);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
+// On-device check of the split GEMM against a double-precision host product (stif_selftest).
+int hp_selftest(std::string& report) {
+  const int M = 300, Ks[2] = {64, 256}, N = 128;
+  int fails = 0;
+  for (int t = 0; t < 2; ++t) {
+    const int K = Ks[t];
+    std::vector<float> A((size_t)M * K), W((size_t)192 * K), b(N);
+    uint32_t s = 12345u + t;
+    auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+    for (auto& x : A) x = rnd();
+    for (auto& x : W) x = 3.0f * rnd();
+    for (auto& x : b) x = rnd();
+    std::vector<uint8_t> hi, lo;
+    split_images(W, 192, K, hi, lo);
+    HpLayer L{nullptr, nullptr, 192, K};
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    cudaMalloc(&L.hi, hi.size()); cudaMalloc(&L.lo, lo.size());
+    cudaMalloc(&dA, A.size() * 4); cudaMalloc(&dB, b.size() * 4); cudaMalloc(&dC, (size_t)M * N * 4);
+    cudaMemcpy(L.hi, hi.data(), hi.size(), cudaMemcpyHostToDevice); cudaMemcpy(L.lo, lo.data(), lo.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(hp_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<64>());
+    cudaFuncSetAttribute(hp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<256>());
+    int64_t launches = 0;
+    LaunchCtx cx{nullptr, &launches, 148};
+    cudaError_t e = hp_gemm(cx, L, 64, N, dA, dB, dC, N, M, 0);       // outputs 64..191 of the layer
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    std::vector<float> C((size_t)M * N);
+    cudaMemcpy(C.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost);
+    double worst = 0.0, ref_max = 0.0;
+    for (int m = 0; m < M; ++m)
+      for (int n = 0; n < N; ++n) {
+        double r = b[n];
+        for (int k = 0; k < K; ++k) r += (double)A[(size_t)m * K + k] * W[(size_t)(64 + n) * K + k];
+        worst = std::max(worst, std::fabs(r - C[(size_t)m * N + n]));
+        ref_max = std::max(ref_max, std::fabs(r));
+      }
+    char line[256];
+    snprintf(line, sizeof line, "T%d split-bf16 GEMM k%d n%d: max_abs_err %.3e (ref max %.3e) %s\n", 4 + t, K, N, worst, ref_max,
+             e == cudaSuccess ? "" : cudaGetErrorString(e));
+    report += line;
+    if (e != cudaSuccess || !(worst <= 2e-4 * ref_max)) ++fails;
+    cudaFree(L.hi); cudaFree(L.lo); cudaFree(dA); cudaFree(dB); cudaFree(dC);
+  }
+  return fails;
+}
+
+}  // namespace stif

@@ -78,6 +78,7 @@ struct stif_decoder {
   float* d_w32 = nullptr;  // fp32 folded weights (one allocation)
   DeviceWeights32 w32{};
   TcWeights* tcw = nullptr;
+  HpWeights* hpw = nullptr;  // split-bf16 images of the dense layers for STIF_MODE_FP32 (kernels_hp.cu)
   std::map<std::array<int, 5>, DeviceGeometry> geos;   // key: H, W, HH, WW, warp-base variant
   std::vector<std::array<int, 5>> geo_order;           // insertion order of `geos` (oldest first): single-entry eviction
   int64_t launches = 0;
@@ -647,6 +648,7 @@ int stif_destroy(stif_decoder_t* d) {
   }
   if (d->d_w32) cudaFree(d->d_w32);
   if (d->tcw) tc_weights_destroy(d->tcw);
+  if (d->hpw) hp_weights_destroy(d->hpw);
   if (d->host_scratch) cudaFree(d->host_scratch);
   if (d->host_stream) cudaStreamDestroy(d->host_stream);
   if (d->h2d_stream) cudaStreamDestroy(d->h2d_stream);
@@ -686,6 +688,13 @@ int stif_load_weights(stif_decoder_t* d, const float* const* tensors, int num_te
   std::string err;
   d->tcw = tc_weights_create(d->hw, err);
   if (!d->tcw) return set_error(STIF_ECUDA, "packing tensor-core weights failed: %s", err.c_str());
+  if (d->hpw) { hp_weights_destroy(d->hpw); d->hpw = nullptr; }
+  d->w32.hp = nullptr;
+  if (!getenv("STIF_FP32_SIMT")) {   // STIF_FP32_SIMT=1 keeps the SIMT SGEMM (test anchor for the tensor-core split GEMM)
+    d->hpw = hp_weights_create(d->hw, err);
+    if (!d->hpw) return set_error(STIF_ECUDA, "packing split-bf16 weights failed: %s", err.c_str());
+    d->w32.hp = d->hpw;
+  }
   CUDA_OR_RETURN(cudaDeviceSynchronize());
   d->weights_loaded = true;
   return STIF_OK;

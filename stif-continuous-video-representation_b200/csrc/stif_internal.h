@@ -37,8 +37,14 @@ struct FoldedWeights {
 // tensors: the 26 host pointers of stif_load_weights, in ABI order.
 void fold_weights(const float* const* tensors, FoldedWeights& out);
 
+// Split-bf16 tensor-core GEMMs of the high-precision mode (kernels_hp.cu): per dense layer the bf16 hi / lo SW128 images.
+struct HpLayer { uint8_t* hi; uint8_t* lo; int N, K; };
+struct HpWeights;
+enum HpLayerId { HP_F1 = 0, HP_F2, HP_F3, HP_L1, HP_L2, HP_E1, HP_E2, HP_E3 };
+
 // Device-side view of the fp32 copy (kernels_fp32.cu).
 struct DeviceWeights32 {
+  const HpWeights* hp = nullptr;   // non-null: the dense layers run on the tensor cores (hp_gemm) instead of the SIMT SGEMM
   const float *w_tab, *w_tab_lat, *w_up, *a_rel, *a_t, *a_b, *f1_w, *f1_b, *f2_w, *f2_b, *f3_w, *f3_b;
   const float *b_t, *b_b, *l1_w, *l1_b, *l2_w, *l2_b, *l3_w, *l3_b;
   const float *e_t, *e_b, *e1_w, *e1_b, *e2_w, *e2_b, *e3_w, *e3_b, *e4_w, *e4_b;
@@ -135,5 +141,14 @@ cudaError_t project_latent_tc(const LaunchCtx& cx, const TcWeights* tw, const fl
                               int W, void* tab /* fp16 [H*W,256] */, int row_begin, int row_end, bool test_variant = false,
                               bool latent_is_bf16 = false);
 int tc_selftest(int device, std::string& report);
+// C[M, N] (row stride ldc) = act(A[M, K] . W[n_off : n_off + N, :]^T + bias): three tcgen05 MMAs per K step on a 2-term bf16
+// split of both operands, fp32 accumulation (<= ~1e-5 relative).  N a multiple of 64, K = the layer's (64 or 256).
+struct FoldedWeights;
+HpWeights* hp_weights_create(const FoldedWeights& hw, std::string& err);
+void hp_weights_destroy(HpWeights*);
+const HpLayer* hp_layer(const HpWeights* w, int id);
+cudaError_t hp_gemm(const LaunchCtx& cx, const HpLayer& L, int n_off, int N, const float* A, const float* bias, float* C, long ldc,
+                    long M, int act);
+int hp_selftest(std::string& report);
 
 }  // namespace stif

@@ -296,6 +296,7 @@ int tc_selftest(int device, std::string& report) {
            d3[9 * 128 + 2], d3[9 * 128 + 3], r3[9 * 128], r3[9 * 128 + 1], r3[9 * 128 + 2], r3[9 * 128 + 3]);
   report += line;
   if (!(e1 < 1e-3 * std::max(1.0, m1)) || !(e2 < 1e-3 * std::max(1.0, m2)) || !(e3 < 1e-3 * std::max(1.0, m3))) rc = -1;
+  if (hp_selftest(report) != 0) rc = -1;   // T4 / T5: the split-bf16 GEMM of the high-precision mode (kernels_hp.cu)
   report += rc == 0 ? "selftest: PASS\n" : "selftest: FAIL\n";
   return rc;
 }
