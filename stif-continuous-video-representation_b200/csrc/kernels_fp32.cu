@@ -7,6 +7,7 @@
 // kernels, not the throughput path.
 //
 // Reference semantics: LunaTokis.decoding, codes/models/modules/Sakuya_arch_test.py:364-459.
+#include <algorithm>
 #include <cstdio>
 
 #include "stif_internal.h"
@@ -109,6 +110,47 @@ GemmArgs dense(const float* A, int K, const float* Wt, const float* bias, void* 
   g.A = A; g.A2 = nullptr; g.sam = K; g.sak = 1; g.ksplit = K;
   g.Wt = Wt; g.bias = bias; g.C = C; g.scm = ldc; g.scn = 1; g.M = M; g.N = N; g.K = K; g.act = act; g.out_half = 0;
   return g;
+}
+
+// The 256 -> 4 (flow) and 256 -> 3 (RGB) output layers: C(m, n) = A[m, :] . W[n, :] + b[n], one warp per row of A (a 1 KB
+// coalesced read; the SGEMM tile wasted 60 of its 64 columns on them and ran at a tenth of the memory rate).
+template <int NOUT>
+__global__ void __launch_bounds__(256) out_layer_kernel(const float* __restrict__ A, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                        float* __restrict__ C, long scm, long scn, long M) {
+  const int lane = threadIdx.x & 31;
+  float w[NOUT][8];
+#pragma unroll
+  for (int n = 0; n < NOUT; ++n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(Wt + n * 256) + lane), b = __ldg(reinterpret_cast<const float4*>(Wt + n * 256) + 32 + lane);
+    w[n][0] = a.x; w[n][1] = a.y; w[n][2] = a.z; w[n][3] = a.w; w[n][4] = b.x; w[n][5] = b.y; w[n][6] = b.z; w[n][7] = b.w;
+  }
+  for (long m = (long)blockIdx.x * 8 + (threadIdx.x >> 5); m < M; m += (long)gridDim.x * 8) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(A + m * 256) + lane), b = __ldg(reinterpret_cast<const float4*>(A + m * 256) + 32 + lane);
+    float s[NOUT];
+#pragma unroll
+    for (int n = 0; n < NOUT; ++n) {
+      float t = a.x * w[n][0];
+      t = fmaf(a.y, w[n][1], t); t = fmaf(a.z, w[n][2], t); t = fmaf(a.w, w[n][3], t);
+      t = fmaf(b.x, w[n][4], t); t = fmaf(b.y, w[n][5], t); t = fmaf(b.z, w[n][6], t); t = fmaf(b.w, w[n][7], t);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      s[n] = t;
+    }
+    if (lane < NOUT) {
+      float v = s[0];
+#pragma unroll
+      for (int n = 1; n < NOUT; ++n) v = lane == n ? s[n] : v;
+      C[m * scm + (long)lane * scn] = v + bias[lane];
+    }
+  }
+}
+template <int NOUT>
+cudaError_t launch_out_layer(const LaunchCtx& cx, const float* A, const float* Wt, const float* bias, float* C, long scm, long scn, long M) {
+  if (M <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)std::min<long>((M + 7) / 8, (long)cx.num_sms * 16);
+  out_layer_kernel<NOUT><<<grid, 256, 0, cx.stream>>>(A, Wt, bias, C, scm, scn, M);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
 }
 
 struct Vec64 { float v[64]; };
@@ -428,7 +470,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(cudaGetLastError());
     STIF_TRY(dense_layer(cx, w, HP_L1, 0, 64, ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 1));
     STIF_TRY(dense_layer(cx, w, HP_L2, 0, 256, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 1));
-    STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, n, 4, 0), false));
+    STIF_TRY(launch_out_layer<4>(cx, ws.act_b, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, 1, n));
   }
   // ---- K2: stage C + D + E over rows [row_begin, row_end)
   for (long q0 = row_begin * WW; stage == 2 && q0 < row_end * WW; q0 += chunk) {
@@ -441,9 +483,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(dense_layer(cx, w, HP_E1, 0, 64, ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 1));
     STIF_TRY(dense_layer(cx, w, HP_E2, 0, 256, ws.act_a, 64, w.e2_w, w.e2_b, ws.act_b, 256, n, 1));
     STIF_TRY(dense_layer(cx, w, HP_E3, 0, 256, ws.act_b, 256, w.e3_w, w.e3_b, ws.act_a, 256, n, 1));
-    GemmArgs g = dense(ws.act_a, 256, w.e4_w, w.e4_b, out_rgb + q0, 1, n, 3, 0);
-    g.scm = 1; g.scn = Qall;  // planar [3,HH,WW] (Sakuya_arch_test.py:457)
-    STIF_TRY(launch_gemm(cx, g, false));
+    STIF_TRY(launch_out_layer<3>(cx, ws.act_a, w.e4_w, w.e4_b, out_rgb + q0, 1, Qall, n));   // planar [3,HH,WW] (Sakuya_arch_test.py:457)
   }
   return cudaSuccess;
 }
@@ -488,7 +528,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
       STIF_TRY(cudaGetLastError());
       STIF_TRY(dense_layer(cx, w, HP_L1, 0, 64, ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 1));
       STIF_TRY(dense_layer(cx, w, HP_L2, 0, 256, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 1));
-      STIF_TRY(launch_gemm(cx, dense(ws.act_b, 256, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, n, 4, 0), false));
+      STIF_TRY(launch_out_layer<4>(cx, ws.act_b, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, 1, n));
     }
     // stage C + D + E into the per-pass prediction, then the area-weighted accumulation
     STIF_TRY(decode_slab_fp32(cx, w, hw, geo, ws, t, 0, geo.HH, 0, geo.HH, ws.pred, 2));
