@@ -398,7 +398,7 @@ def main_ours(args):
     achieved = flop_launch / (per[dom] * 1e-3) / 1e12
     kernel_ms = sum(prof["ms"]) / args.steps
     traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (config 2 only)
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if args.workload == "config2" and os.path.isfile(tpath):
         t = json.load(open(tpath)).get(dom)
         if t:

@@ -307,6 +307,20 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
 #endif
 }
 
+// Long waits (a workgroup of the rotation kernels waiting for a TMEM slot: thousands of clocks): back off between probes so
+// that eight spinning warps do not take issue slots from the sixteen that hold the slots (the spin loop was 25 % of K1's
+// executed instructions).  STIF_LONG_WAIT_NS = 0 falls back to the plain loop.
+#ifndef STIF_LONG_WAIT_NS
+#define STIF_LONG_WAIT_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+  if (STIF_LONG_WAIT_NS == 0) { mbar_wait_or_trap(bar, parity); return; }
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    __nanosleep(STIF_LONG_WAIT_NS);
+    if (it > (1u << 22)) __trap();
+  }
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t p;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p));
@@ -761,13 +775,17 @@ __global__ void __launch_bounds__(512, 1) k0_project_kernel(const __grid_constan
   float v[48], f[6];
   auto fetch = [&](long tile) {
     const long m = min(p.m_begin + tile * kTile + row, p.m_end - 1);
+    if (p.latent16) {   // (uniform: one branch per tile, not per element)
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+      for (int i = 0; i < 6; ++i)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const long at = (long)((part + 4 * i) * 8 + e) * p.HW + m;
-        v[8 * i + e] = p.latent16 ? __uint_as_float((uint32_t)__ldg(p.latent16 + at) << 16) : __ldg(p.latent + at);
-      }
+        for (int e = 0; e < 8; ++e) v[8 * i + e] = __uint_as_float((uint32_t)__ldg(p.latent16 + (long)((part + 4 * i) * 8 + e) * p.HW + m) << 16);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[8 * i + e] = __ldg(p.latent + (long)((part + 4 * i) * 8 + e) * p.HW + m);
+    }
     if (part == 0) {
 #pragma unroll
       for (int e = 0; e < 6; ++e) f[e] = __ldg(p.frames + (long)e * p.HW + m);
@@ -1116,13 +1134,13 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
       }
       trace_mark(cx, 2);
       if (seq > 0) {
-        mbar_wait_or_trap(&h2_read[slot], (seq - 1) & 1);   // the slot's previous tile no longer reads columns [0, 96)
+        mbar_wait_long(&h2_read[slot], (seq - 1) & 1);   // the slot's previous tile no longer reads columns [0, 96)
         tc_fence_after();
       }
       tmem_st16(cx.lane_addr + kColH0 + CH * 16, pk);
       tmem_st_wait();
       tc_fence_before();
-      if (seq > 0) mbar_wait_or_trap(&slot_free[slot], (seq - 1) & 1);   // ... and has left the slot and its named barriers
+      if (seq > 0) mbar_wait_long(&slot_free[slot], (seq - 1) & 1);   // ... and has left the slot and its named barriers
     }
     step_done<ISSUER>(cx);
     trace_mark(cx, 3);
@@ -1434,7 +1452,8 @@ __device__ __forceinline__ uint4 ldg128_hint(const uint4* p) {
 }
 
 // phase 2 (loads + blend + sine -> A tile)
-template <class Sig>
+// UADD (compile time: the hook costs registers the default kernel does not have): + p.uadd[q], decoding_test away from x4
+template <bool UADD = false, class Sig>
 __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane, Sig&& loads_issued,
                                                 long tile = 0) {
   const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
@@ -1494,7 +1513,7 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
         acc[2 * e + 1] = add_f16((uint16_t)(a >> 16), cE[2 * e + 1]);
       }
       const int r = warp_in_wg * 16 + (s_ >> 1) * 4 + (lane >> 3);
-      if (p.uadd) {   // decoding_test away from x4: + bilinear(UE1; g1) + bilinear(UE2; g2), precomputed per query (warp_u_terms)
+      if constexpr (UADD) {   // decoding_test away from x4: + bilinear(UE1; g1) + bilinear(UE2; g2), precomputed per query (warp_u_terms)
         bool valid_;
         int jy_, jx_;
         const long q_ = k2_query(p, tile, r, valid_, jy_, jx_);
@@ -1554,7 +1573,7 @@ __device__ __forceinline__ void k2_tile_loop(const K2Params& p, const CtaSetup& 
     // ---- stage C + D + first layer of encode_imnet (hoisted)                         (:424-456)
     trace_mark(cx, 1);
     if constexpr (!ISSUER) {
-      k2_gather_blend(p, a0, stg, warp_in_wg, lane, [&]() { gather_turn_done(cx, tile == tile_first); }, tile);
+      k2_gather_blend(p, a0, stg, warp_in_wg, lane, [&]() { gather_turn_done(cx, tile == tile_first); });
       fence_proxy_async_smem();
       tc_fence_before();
     }
@@ -1630,7 +1649,7 @@ __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_const
 // the next tile's workgroup waits for that before its first arrival on the same named barriers.  Counters restart per
 // tile: 10 step barriers (even, so the id alternation restarts at 0) and 9 accumulator chunks per tile (the ring position
 // of tile k of a slot is 9 k).
-template <bool ISSUER, bool BAND>
+template <bool ISSUER, bool BAND, bool UADD>
 __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx, int me) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
@@ -1667,11 +1686,11 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     trace_mark(cx, 1);
     if constexpr (!ISSUER) {
       // ---- gather phase: no tensor memory, no named barrier of the slot                       (:424-456)
-      k2_gather_blend(p, a0, stg, warp_in_wg, lane, []() {}, tile);
+      k2_gather_blend<UADD>(p, a0, stg, warp_in_wg, lane, []() {}, tile);
       fence_proxy_async_smem();
       tc_fence_before();
       trace_mark(cx, 2);
-      if (seq > 0) mbar_wait_or_trap(&slot_free[slot], (seq - 1) & 1);   // the slot's previous tile has left it
+      if (seq > 0) mbar_wait_long(&slot_free[slot], (seq - 1) & 1);   // the slot's previous tile has left it
       tc_fence_after();
     }
     step_done<ISSUER>(cx);
@@ -1708,7 +1727,7 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
   }
 }
 
-template <bool BAND>
+template <bool BAND, bool UADD = false>
 __global__ void __launch_bounds__(832, 1) k2_stage_cde_rot_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2rBars, 0, p.wimg, k2WBytes, 512);
   {
@@ -1719,8 +1738,8 @@ __global__ void __launch_bounds__(832, 1) k2_stage_cde_rot_kernel(const __grid_c
   WgCtx cx = make_wg(s);   // warps 0, 1: issuers (cx.wg = TMEM slot); warps 2..25: workgroups 0..2
   if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (cx.issuer ? 24 + cx.wg : cx.slot) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
-  if (cx.issuer) k2_rot_loop<true, BAND>(p, s, cx, cx.wg);
-  else k2_rot_loop<false, BAND>(p, s, cx, cx.wg);
+  if (cx.issuer) k2_rot_loop<true, BAND, UADD>(p, s, cx, cx.wg);
+  else k2_rot_loop<false, BAND, UADD>(p, s, cx, cx.wg);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -1800,6 +1819,8 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_ensemble_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (getenv("STIF_DEBUG_ATTRS")) {
@@ -1966,8 +1987,10 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
   const bool band = k1_row_begin > 0 || k1_row_end < geo.HH;   // stage A+B rows are incomplete: check every weighted tap
 #if STIF_K2_ROT
   const int grid_rot = (int)std::min<long>(cx.num_sms, ntiles);
-  if (cudaError_t e = band ? launch_pdl(k2_stage_cde_rot_kernel<true>, grid_rot, 832, k2rSmem, cx.stream, p)
-                           : launch_pdl(k2_stage_cde_rot_kernel<false>, grid_rot, 832, k2rSmem, cx.stream, p))
+  if (cudaError_t e = p.uadd ? (band ? launch_pdl(k2_stage_cde_rot_kernel<true, true>, grid_rot, 832, k2rSmem, cx.stream, p)
+                                     : launch_pdl(k2_stage_cde_rot_kernel<false, true>, grid_rot, 832, k2rSmem, cx.stream, p))
+                      : band   ? launch_pdl(k2_stage_cde_rot_kernel<true>, grid_rot, 832, k2rSmem, cx.stream, p)
+                               : launch_pdl(k2_stage_cde_rot_kernel<false>, grid_rot, 832, k2rSmem, cx.stream, p))
     return e;
 #else
   if (cudaError_t e = band ? launch_pdl(k2_stage_cde_kernel<true>, grid, 576, k2Smem, cx.stream, p)
