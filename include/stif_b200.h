@@ -171,6 +171,20 @@ int stif_decode_host_bf16(stif_decoder_t* dec,
                           const float* times_host, int T, int mode,
                           void* out_rgb_host);
 
+/* ---- the step before the path: the encoder's modulated deformable convolution ----
+ * Forward of DCNv2 behind the call signature of the reference's extension entry `_ext.dcn_v2_forward(input, weight, bias,
+ * offset, mask, kh, kw, sh, sw, ph, pw, dh, dw, dg)` (codes/models/modules/DCNv2/dcn_v2.py:24-27 -> src/cuda/dcn_v2_cuda.cu:42-172,
+ * im2col src/cuda/dcn_v2_im2col_cuda.cu:125-195).  All pointers are DEVICE pointers, fp32, contiguous NCHW:
+ *   input [B,C,H,W], weight [Cout,C,kh,kw], bias [Cout], offset [B, dg*2*kh*kw, H, W] (channel g*2*kh*kw + 2k = dy, +1 = dx of
+ *   tap k), mask [B, dg*kh*kw, H, W], out [B,Cout,H,W]; stream-ordered on `stream`.
+ * Implemented: the one geometry the reference's encoder uses (C = Cout = 64, 3x3, stride 1, padding 1, dilation 1, dg = 8;
+ * Sakuya_arch_test.py:38-66,135-160) as a fused deformable-im2col + tcgen05 kernel with a 2-term bf16 operand split
+ * (fp32-class accuracy).  Any other geometry returns STIF_EINVAL without touching `out`: the caller keeps its fallback. */
+int stif_dcn_v2_forward(const float* input_dev, const float* weight_dev, const float* bias_dev,
+                        const float* offset_dev, const float* mask_dev,
+                        int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                        int dg, float* out_dev, void* stream);
+
 /* ---- introspection used by the parity tests (same device functions as the decode path) ---- */
 
 /* Per-axis query tables for an (n_lr -> n_hr) axis, HOST outputs of length n_hr (any may be NULL):

@@ -8,7 +8,7 @@ NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 CXXFLAGS="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off,-Wall"
 pids=()
-for f in stif_api.cu kernels_fp32.cu kernels_tc.cu kernels_hp.cu tc_selftest.cu; do
+for f in stif_api.cu kernels_fp32.cu kernels_tc.cu kernels_hp.cu kernels_dcn.cu tc_selftest.cu; do
   ( "$NVCC" $ARCH $CXXFLAGS ${EXTRA_NVCC_FLAGS:-} -c "$HERE/$f" -o "$HERE/obj/${f%.cu}.o" ) &
   pids+=($!)
 done

@@ -27,7 +27,7 @@ STIF_ABI_VERSION = 2
 # every symbol include/stif_b200.h declares (tests/test_abi.py checks the .so exports them all)
 EXPORTS = [
     "stif_abi_version", "stif_last_error", "stif_create", "stif_destroy", "stif_load_weights",
-    "stif_prepare", "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_window", "stif_decode_host", "stif_decode_host_bf16", "stif_axis_tables",
+    "stif_prepare", "stif_workspace_bytes", "stif_decode", "stif_decode_rows", "stif_decode_window", "stif_decode_host", "stif_decode_host_bf16", "stif_dcn_v2_forward", "stif_axis_tables",
     "stif_ensemble_weights", "stif_debug_last_flow", "stif_debug_host_pipeline", "stif_debug_band_plan", "stif_launch_count", "stif_profile_enable", "stif_profile_read", "stif_selftest",
 ]
 
@@ -59,6 +59,7 @@ def _load():
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp]
     lib.stif_decode_host.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, vp]
     lib.stif_decode_host_bf16.argtypes = lib.stif_decode_host.argtypes
+    lib.stif_dcn_v2_forward.argtypes = [vp] * 5 + [C.c_int] * 14 + [vp, vp]
     lib.stif_axis_tables.argtypes = [C.c_int, C.c_int, fp, ip, fp, fp]
     lib.stif_ensemble_weights.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_size_t]
     lib.stif_debug_last_flow.argtypes = [vp, fp, C.c_size_t]
@@ -126,3 +127,23 @@ def band_plan(H: int, W: int, HH: int, WW: int, T: int = 2, bands: int = 6, forc
     if n < 0:
         check(n)
     return a[:n].copy(), b[:n].copy(), c[:n].copy(), float(cost.value)
+
+
+def dcn_v2_forward(input, weight, bias, offset, mask, kh, kw, sh, sw, ph, pw, dh, dw, dg):
+    """``_ext.dcn_v2_forward`` (``DCNv2/dcn_v2.py:24-27``) on the B200 kernel; torch CUDA tensors in, a new tensor out.
+    Returns ``None`` when the geometry is not the reference encoder's (the caller keeps its fallback)."""
+    import torch
+
+    if not (input.is_cuda and input.dtype == torch.float32):
+        return None
+    B, Cin, H, W = input.shape
+    Cout = weight.shape[0]
+    if (Cin, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg) != (64, 64, 3, 3, 1, 1, 1, 1, 1, 1, 8):
+        return None
+    t = [x.contiguous().float() for x in (input, weight, bias, offset, mask)]
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=input.device)
+    with torch.cuda.device(input.device):
+        rc = lib.stif_dcn_v2_forward(*[x.data_ptr() for x in t], B, Cin, H, W, Cout, kh, kw, sh, sw, ph, pw, dh, dw, dg,
+                                     out.data_ptr(), torch.cuda.current_stream(input.device).cuda_stream)
+    check(rc)
+    return out

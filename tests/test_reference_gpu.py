@@ -180,9 +180,9 @@ def test_ensemble_weights_bit_equal_to_reference_on_gpu(stif, ref_models):
 
 
 # ---------------------------------------------------------------------------------------- config 5
-def _run_tool(workdir, mode, frames, report):
+def _run_tool(workdir, mode, frames, report, dcn="torchvision"):
     cmd = [sys.executable, os.path.join(ROOT, "tools", "run_custom_video_test.py"), "--mode", mode, "--make-video", str(frames),
-           "--report", report]
+           "--report", report, "--dcn", dcn]
     env = dict(os.environ)
     env.pop("CUDA_VISIBLE_DEVICES", None)
     p = subprocess.run(cmd, cwd=workdir, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
@@ -249,3 +249,50 @@ def test_config5_full_99_frame_sequence(tmp_path):
     print(f"config5 full: 98 pairs, decoder median {np.median(dec) * 1e3:.2f} ms/pair ({q / np.median(dec):.3e} q/s incl. python), "
           f"encoder median {np.median(rep['encoder_s']) * 1e3:.1f} ms/pair, script wall {rep['wall_s']:.1f} s")
     _save("config5_full.json", rep)
+
+
+# ---------------------------------------------------------------------------------------- the step before the path: DCNv2
+@pytest.mark.parametrize("B,H,W,off_scale", [(1, 24, 40, 1.0), (2, 17, 23, 4.0), (3, 68, 120, 12.0), (1, 272, 480, 2.0)])
+def test_dcn_v2_forward_matches_deform_conv2d(B, H, W, off_scale, stif):
+    """`stif_dcn_v2_forward` (fused deformable im2col + split-bf16 tcgen05 GEMM) against `torchvision.ops.deform_conv2d`, the
+    implementation the reference's `_ext.dcn_v2_forward` is served by on torch >= 1.11 (same offset / mask layout and zero
+    padding as DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:125-195): the encoder's geometry, sizes that are not multiples of the
+    128-pixel tile, batches, offsets large enough to leave the image."""
+    from torchvision.ops import deform_conv2d
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H)
+    x = torch.randn(B, 64, H, W, device="cuda", generator=g)
+    w = torch.randn(64, 64, 3, 3, device="cuda", generator=g) / 24.0
+    b = torch.randn(64, device="cuda", generator=g)
+    off = off_scale * torch.randn(B, 144, H, W, device="cuda", generator=g)
+    m = torch.sigmoid(torch.randn(B, 72, H, W, device="cuda", generator=g))
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = deform_conv2d(x, off, w, b, stride=1, padding=1, dilation=1, mask=m)
+    out = stif.dcn_v2_forward(x, w, b, off, m, 3, 3, 1, 1, 1, 1, 1, 1, 8)
+    torch.cuda.synchronize()
+    assert out is not None and out.shape == ref.shape
+    err = float((out - ref).abs().max())
+    print(f"dcn_v2 B={B} {H}x{W} offsets x{off_scale}: max-abs {err:.3e} (|ref| max {float(ref.abs().max()):.2f})")
+    assert err <= 2e-4 * max(1.0, float(ref.abs().max()))
+    assert stif.dcn_v2_forward(x[:, :32], w[:, :32], b, off, m, 3, 3, 1, 1, 1, 1, 1, 1, 8) is None      # other geometries: caller's fallback
+
+
+@pytest.mark.timeout(900, method="thread")
+def test_config5_with_b200_dcn_in_the_encoder(tmp_path):
+    """Config 5 with BOTH sides of the boundary on this repo's kernels: the reference's encoder calls `_ext.dcn_v2_forward`
+    78 times per pair -> `stif_dcn_v2_forward`; decoder patched.  JPEGs against the untouched reference (torchvision DCN +
+    reference decoder) on 3 pairs; encoder seconds per pair reported for both DCN implementations."""
+    _need_ref()
+    a, b = tmp_path / "b200", tmp_path / "plain"
+    for d in (a, b):
+        d.mkdir()
+        _write_full_state_dict(str(d))
+    rep_a = _run_tool(str(a), "bf16", 4, str(a / "report.json"), dcn="b200")
+    rep_b = _run_tool(str(b), "reference", 4, str(b / "report.json"))
+    assert rep_a["dcn_calls"]["b200"] == 3 * 78 and rep_a["dcn_calls"]["torchvision"] == 0
+    ps = _jpeg_psnr(str(a / "output/train/HR"), str(b / "output/train/HR"), 24)
+    ea, eb = np.median(rep_a["encoder_s"][1:]), np.median(rep_b["encoder_s"][1:])
+    print(f"config5 with the B200 DCNv2 in the encoder: JPEG PSNR vs untouched reference min {min(ps):.1f} dB; "
+          f"encoder s/pair {ea:.4f} (b200 dcn) vs {eb:.4f} (torchvision dcn)")
+    _save("config5_b200_dcn.json", {"psnr_db": ps, "b200": rep_a, "reference": rep_b})
+    assert min(ps) >= 35.0

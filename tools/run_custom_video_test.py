@@ -14,7 +14,7 @@ does, all outside the reference's files:
   3. `runpy`-executes the script from the current directory.
 
     python tools/run_custom_video_test.py [--reference DIR] --mode bf16|fp32|reference [--synthetic-weights]
-                                          [--make-video N] [--report out.json]
+                                          [--make-video N] [--report out.json] [--dcn torchvision|b200]
 
 `--mode reference` leaves the decoder untouched (the unpatched A/B arm).  `--report` writes encoder / decoder seconds
 per frame pair (CUDA-synchronised around `gen_feat` and `decoding`) and the script's wall time.
@@ -39,12 +39,22 @@ def default_reference() -> str:
     return staged if os.path.isdir(os.path.join(staged, "codes")) else "/root/reference"
 
 
-def make_ext_shim():
+def make_ext_shim(dcn: str = "torchvision"):
+    """`_ext` for the reference's encoder.  dcn='torchvision': `torchvision.ops.deform_conv2d`; dcn='b200': this repo's sm_100a
+    kernel (`stif_dcn_v2_forward`, the encoder's 64->64 3x3 dg=8 geometry; anything else still goes to torchvision)."""
     from torchvision.ops import deform_conv2d
 
     ext = types.ModuleType("_ext")
+    ext.calls = {"b200": 0, "torchvision": 0}
 
     def dcn_v2_forward(input, weight, bias, offset, mask, kh, kw, sh, sw, ph, pw, dh, dw, dg):
+        if dcn == "b200":
+            import stif_b200
+            out = stif_b200.dcn_v2_forward(input, weight, bias, offset, mask, kh, kw, sh, sw, ph, pw, dh, dw, dg)
+            if out is not None:
+                ext.calls["b200"] += 1
+                return out
+        ext.calls["torchvision"] += 1
         return deform_conv2d(input, offset, weight, bias, stride=(sh, sw), padding=(ph, pw), dilation=(dh, dw), mask=mask)
 
     def unsupported(*a, **k):
@@ -86,11 +96,13 @@ def main():
     ap.add_argument("--make-video", type=int, default=0, metavar="N", help="write N synthetic 960x540 frames if video_sequences/train is missing")
     ap.add_argument("--time-decoder", action="store_true", help="print decoder seconds per frame pair")
     ap.add_argument("--report", default=None, help="write encoder/decoder seconds per pair + wall time as JSON")
+    ap.add_argument("--dcn", default="torchvision", choices=["torchvision", "b200"],
+                    help="what serves the encoder's `_ext.dcn_v2_forward`: torchvision.ops.deform_conv2d or this repo's sm_100a kernel")
     args = ap.parse_args()
 
     import torch
 
-    sys.modules["_ext"] = make_ext_shim()
+    sys.modules["_ext"] = make_ext_shim(args.dcn)
     codes = os.path.join(os.path.abspath(args.reference), "codes")
     if not os.path.isfile(os.path.join(codes, "custom_video_test.py")):
         raise SystemExit(f"no reference under {args.reference} (run `python -m oracle.stage_ref` in the build container)")
@@ -136,6 +148,8 @@ def main():
     runpy.run_path(os.path.join(codes, "custom_video_test.py"), run_name="__main__")
     report["wall_s"] = time.perf_counter() - t0
     report["pairs"] = len(report["decoder_s"])
+    report["dcn"] = args.dcn
+    report["dcn_calls"] = dict(sys.modules["_ext"].calls)
     if args.mode != "reference":
         import stif_b200
         report["native_lib"] = stif_b200.LIB_PATH
