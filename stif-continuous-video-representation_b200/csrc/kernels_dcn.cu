@@ -25,7 +25,7 @@ namespace {
 using namespace tc;
 
 struct DcnParams {
-  const float* input;    // [B, 64, H, W]
+  const float* input;    // [B, 8 groups, H * W, 8 channels]: the group-major channels-last copy of the NCHW input (dcn_pack_input_kernel)
   const float* weight;   // [64, 64, 3, 3]
   const float* bias;     // [64]
   const float* offset;   // [B, 8 * 2 * 9, H, W]   channel (g * 18 + 2 k) = dy, (+ 1) = dx of tap k = i * 3 + j   (im2col :162-167)
@@ -109,14 +109,16 @@ __global__ void __launch_bounds__(512, 1) dcn_v2_forward_kernel(const __grid_con
             const bool t3 = h_low + 1 <= p.H - 1 && w_low >= 0, t4 = h_low + 1 <= p.H - 1 && w_low + 1 <= p.W - 1;
             const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
             const long o1 = (long)h_low * p.W + w_low;
-            const float* src = p.input + (long)(b * 64 + g * 8) * HW;
+            // one 32-byte load per corner: the 8 channels of this deformable group are contiguous in the packed copy (the
+            // NCHW original needs 8 scalar loads per corner, each up to 32 L1 wavefronts when the offsets scatter the lanes)
+            const float* src = p.input + ((long)(b * 8 + g) * HW) * 8;
+            const U8x32 z{};
+            const U8x32 c1 = t1 ? ldg256(src + o1 * 8) : z, c2 = t2 ? ldg256(src + (o1 + 1) * 8) : z;
+            const U8x32 c3 = t3 ? ldg256(src + (o1 + p.W) * 8) : z, c4 = t4 ? ldg256(src + (o1 + p.W + 1) * 8) : z;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const float* s = src + (long)c * HW;
-              const float v1 = t1 ? __ldg(s + o1) : 0.f, v2 = t2 ? __ldg(s + o1 + 1) : 0.f;
-              const float v3 = t3 ? __ldg(s + o1 + p.W) : 0.f, v4 = t4 ? __ldg(s + o1 + p.W + 1) : 0.f;
-              v[c] = (w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4) * m;                                   // (:44-50, :190)
-            }
+            for (int c = 0; c < 8; ++c)
+              v[c] = (w1 * __uint_as_float(c1.r[c]) + w2 * __uint_as_float(c2.r[c]) + w3 * __uint_as_float(c3.r[c]) +
+                      w4 * __uint_as_float(c4.r[c])) * m;                                             // (:44-50, :190)
           }
         }
         uint32_t hi[4], lo[4];
@@ -172,6 +174,22 @@ __global__ void __launch_bounds__(512, 1) dcn_v2_forward_kernel(const __grid_con
   if (warp == 0) tmem_dealloc(tmem, 64);
 }
 
+// NCHW [B, 64, H, W] -> [B, 8 groups, H * W, 8 channels]: thread = (b, g, pixel); reads coalesced along the pixel axis per
+// channel, writes one 32-byte sector.
+__global__ void dcn_pack_input_kernel(const float* __restrict__ in, float* __restrict__ out, long HW, long n) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long bg = i / HW, pix = i - bg * HW;
+  uint32_t v[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v[c] = __float_as_uint(__ldg(in + (bg * 8 + c) * HW + pix));
+  stg256(out + i * 8, v);
+}
+
+// scratch for the packed input, one per device, grown on demand (the only state of this entry point)
+struct DcnScratch { float* buf = nullptr; size_t bytes = 0; };
+DcnScratch g_dcn_scratch[64];
+
 }  // namespace
 }  // namespace stif
 
@@ -190,7 +208,19 @@ extern "C" int stif_dcn_v2_forward(const float* input, const float* weight, cons
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STIF_ECUDA;
   const long ntiles = ((long)B * H * W + 127) / 128;
-  DcnParams p{input, weight, bias, offset, mask, out, B, H, W};
+  if (dev < 0 || dev >= 64) return STIF_EINVAL;
+  DcnScratch& sc = g_dcn_scratch[dev];
+  const size_t need = (size_t)B * 64 * H * W * sizeof(float);
+  if (sc.bytes < need) {
+    if (sc.buf) cudaFree(sc.buf);
+    sc.buf = nullptr;
+    sc.bytes = 0;
+    if (cudaMalloc(&sc.buf, need) != cudaSuccess) return STIF_ECUDA;
+    sc.bytes = need;
+  }
+  const long npack = (long)B * 8 * H * W;
+  dcn_pack_input_kernel<<<(unsigned)((npack + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, sc.buf, (long)H * W, npack);
+  DcnParams p{sc.buf, weight, bias, offset, mask, out, B, H, W};
   dcn_v2_forward_kernel<<<(unsigned)std::min<long>(sms, ntiles), 512, dSmem, (cudaStream_t)stream>>>(p);
   return cudaGetLastError() == cudaSuccess ? STIF_OK : STIF_ECUDA;
 }
