@@ -63,8 +63,9 @@ HostBandPlan plan_host_bands(int H, int W, int HH, int WW, int G, int bands_hint
       const int h0 = k ? pl.he[k - 1] : 0, g0 = k ? pl.ge[k - 1] : 0, l0 = k ? pl.lr_end[k - 1] : 0;
       t = std::max(t, (double)pl.lr_end[k] * W * 198 * 4 / 55e3);
       if (pl.lr_end[k] > l0) t += 11.0 + 0.3 * (pl.lr_end[k] - l0) * W / 1000.0;   // K0: fixed + ~0.3 ns per texel
-      if (pl.he[k] > h0) t += G * (4.3 * std::ceil((double)k1_tiles(pl.he[k] - h0) / slots) + 19.0);
-      if (pl.ge[k] > g0) t += G * (3.9 * std::ceil((double)k2_tiles(pl.ge[k] - g0) / slots) + 19.0);
+      // (the G resident timesteps of a band share one launch per stage: decode_multi_tc)
+      if (pl.he[k] > h0) t += 4.3 * std::ceil((double)G * k1_tiles(pl.he[k] - h0) / slots) + 19.0;
+      if (pl.ge[k] > g0) t += 3.9 * std::ceil((double)G * k2_tiles(pl.ge[k] - g0) / slots) + 19.0;
     }
     t += (double)(HH - (nb > 1 ? pl.ge[nb - 2] : 0)) * WW * 12 * G / 55e3;
     pl.cost_us = t;

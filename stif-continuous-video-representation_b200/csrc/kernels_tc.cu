@@ -85,8 +85,16 @@ struct alignas(16) K2Consts {
   float e1_b[64], e2_b[256], e3_b[256];
   float e4_w[3 * 256], e4_b[4];
 };
+// MULTI launches (band-major host pipeline): one launch covers the same rows of up to four timesteps ("slabs"), each with its
+// own time constants and tables; tile t of the launch is tile t % tiles_per_slab of slab t / tiles_per_slab.  Halves the
+// launch count of a band, and with it the pipeline fill / drain each persistent launch pays (~25-45 us).
+constexpr int kMaxSlabs = kMaxSlabsHost;
+struct K1Slab { float cA[64]; float cB[64]; __half* qtab; float* flow; };
+struct K2Slab { float cE[64]; const __half* qtab; const float* flow; float* out; uint8_t* out_u8; };
 struct K1Params {
   K1Consts c;
+  K1Slab slab[kMaxSlabs];     // MULTI launches only
+  long tiles_per_slab, ntiles_total;
   Geometry g;
   const __half* tab;   // [H*W,256]   TA | TB | TE1 | TE2
   __half* qtab;        // [HH*WW,128] Q1 | Q2
@@ -99,6 +107,8 @@ struct K1Params {
 };
 struct K2Params {
   K2Consts c;
+  K2Slab slab[kMaxSlabs];     // MULTI launches only
+  long tiles_per_slab, ntiles_total;
   Geometry g;
   const __half* tab;
   const __half* qtab;
@@ -141,6 +151,8 @@ struct WgCtx {
   int slot;            // logical warp slot: 0..15 epilogue warps (WG0 then WG1), 16/17 the issuers (trace rows, per-warp smem)
   bool issuer;         // this warp only issues the WG's MMAs (warps 0, 1); the other 8 warps of the WG only run epilogues
   uint64_t* extra_commit;   // issuer only: a second mbarrier every chunk's tcgen05.commit also arrives on while it is set
+  uint32_t bias_smem;       // issuer only: shared address of the current layer's bias blocks (one K = 16 block per chunk), 0 = none
+  uint32_t ones_smem;       // issuer only: the constant A tile of the bias K step
   long long* trace;    // this thread's trace cursor (null unless tracing)
 };
 
@@ -327,6 +339,7 @@ __device__ __forceinline__ bool elect_one() {
   return p != 0;
 }
 
+constexpr uint32_t kBiasBlock = 64 * 32, kOnesTile = 128 * 32;   // interleaved K = 16 operands (tc_primitives.cuh: nosw_offset)
 // Issue the MMAs of one 64-wide output chunk and commit to the slot's barrier.  Executed by warp 0 of
 // the WG with warp-uniform operands (one elected lane issues), so the descriptors live in uniform
 // registers and each tcgen05.mma costs a couple of instructions.
@@ -349,6 +362,8 @@ __device__ __forceinline__ void issue_chunk(WgCtx& cx, uint32_t a_base, uint32_t
         if (A_SMEM) umma_ss(d, a0 + 2 * j, bdesc, idesc, j > 0);
         else umma_ts(d, a_base + 8 * j, bdesc, idesc, j > 0);
       }
+      // bias as one more K step: [1 1 1 0 ..] x [hi lo lo2 0 ..]^T accumulates bias[n] (exact: three bf16 terms) into every row
+      if (cx.bias_smem) umma_ss(d, make_desc_nosw(cx.ones_smem), make_desc_nosw(cx.bias_smem + (uint32_t)chunk * kBiasBlock), idesc, true);
       umma_commit(&cx.full[slot]);
       if (cx.extra_commit) umma_commit(cx.extra_commit);
     }
@@ -612,6 +627,7 @@ __device__ __forceinline__ void run_layer2(WgCtx& cx, uint32_t a_base, uint32_t 
 }
 
 // act = sin(acc + bias) -> bf16 -> 8 TMEM columns at dst (no wait: layer_finish2 waits once per late chunk)
+template <bool BIAS = true>
 __device__ __forceinline__ void epi16_sin_to_tmem(const uint32_t (&v)[16], uint32_t dst, const float* __restrict__ bias) {
   uint32_t pk[8];
 #ifdef STIF_DIAG_SKELETON   // diagnostic (WRONG results): the MMA / TMEM / barrier protocol alone
@@ -620,6 +636,12 @@ __device__ __forceinline__ void epi16_sin_to_tmem(const uint32_t (&v)[16], uint3
   tmem_st8(dst, pk);
   return;
 #endif
+  if constexpr (!BIAS) {   // the bias arrived through the MMAs (issue_chunk, bias_smem)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(fast_sin(__uint_as_float(v[2 * j])), fast_sin(__uint_as_float(v[2 * j + 1])));
+    tmem_st8(dst, pk);
+    return;
+  }
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     const float4 b4 = ldc4(bias + 4 * j4);
@@ -631,7 +653,7 @@ __device__ __forceinline__ void epi16_sin_to_tmem(const uint32_t (&v)[16], uint3
   tmem_st8(dst, pk);
 }
 // act = sin(acc + bias) in fp32, contracted with the NOUT x 256 output layer on the FMA pipe
-template <int NOUT>
+template <int NOUT, bool BIAS = true>
 __device__ __forceinline__ void epi16_sin_fma(const uint32_t (&v)[16], const float* __restrict__ bias, const float* __restrict__ w,
                                               float2 (&acc)[NOUT]) {
 #ifdef STIF_DIAG_SKELETON
@@ -640,14 +662,14 @@ __device__ __forceinline__ void epi16_sin_fma(const uint32_t (&v)[16], const flo
 #endif
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
-    const float4 b4 = ldc4(bias + 4 * j4);
+    const float4 b4 = BIAS ? ldc4(bias + 4 * j4) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 w4[NOUT];
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) w4[k] = ldc4(w + k * 256 + 4 * j4);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float2 s = add2(make_float2(__uint_as_float(v[4 * j4 + 2 * h]), __uint_as_float(v[4 * j4 + 2 * h + 1])),
-                      h ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
+      float2 s = make_float2(__uint_as_float(v[4 * j4 + 2 * h]), __uint_as_float(v[4 * j4 + 2 * h + 1]));
+      if constexpr (BIAS) s = add2(s, h ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
       s.x = fast_sin(s.x);
       s.y = fast_sin(s.y);
 #pragma unroll
@@ -656,12 +678,19 @@ __device__ __forceinline__ void epi16_sin_fma(const uint32_t (&v)[16], const flo
   }
 }
 // acc + bias -> fp16 -> 32 bytes of the projected HR table (one full sector)
+template <bool BIAS = true>
 __device__ __forceinline__ void epi16_store_qtab(const uint32_t (&v)[16], const float* __restrict__ bias, __half* dst, bool valid) {
   uint32_t o[8];
 #ifdef STIF_DIAG_SKELETON
   if (v[0] == 0x12345678u) stg256(dst, v);
   return;
 #endif
+  if constexpr (!BIAS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = pack_half2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    if (valid) stg256(dst, o);
+    return;
+  }
 #pragma unroll
   for (int j4 = 0; j4 < 4; ++j4) {
     const float4 b4 = ldc4(bias + 4 * j4);
@@ -754,6 +783,8 @@ __device__ __forceinline__ WgCtx make_wg(const CtaSetup& s) {
   cx.n_issued = cx.n_waited = cx.n_steps = 0;
   cx.trace = nullptr;
   cx.extra_commit = nullptr;
+  cx.bias_smem = 0;
+  cx.ones_smem = 0;
   return cx;
 }
 
@@ -1075,15 +1106,27 @@ __global__ void __launch_bounds__(576, 1) k1_stage_ab_kernel(const __grid_consta
 // (its sum has to live somewhere until the composed layer's F chunk arrives: as fp16 pairs in 16 registers here, the
 // kernel runs at 72 registers per thread).  13 accumulator chunks and 14 step barriers per tile.
 constexpr uint32_t kColH0 = 0;
-constexpr uint32_t k1rPart = k1WBytes, k1rConst = k1rPart + 3 * 128 * 16, k1rBars = k1rConst + kc1Floats * 4, k1rSmem = k1rBars + 128;
+#ifndef STIF_K1_BIAS_MMA
+// 1: the biases of the 13 MMA chunks ride the tensor pipe as an extra K = 16 step (constant ones tile x [hi lo lo2] bias block,
+// interleaved no-swizzle operands; stif_selftest T6) instead of LDCU + MOV + FADD2 per accumulator pair.  Parity-green, 18 % fewer
+// epilogue instructions -- and no faster (K1 0.562 vs 0.560 ms): each extra MMA costs its 32-clock floor on the serial
+// issue -> MMA -> epilogue chain (+0.021 ms) and the shorter epilogues give back only 0.015 ms.  Off by default.
+#define STIF_K1_BIAS_MMA 0
+#endif
+constexpr bool kK1BiasMma = STIF_K1_BIAS_MMA != 0;
+// ... | ones tile | 13 bias blocks (F1, F2 x4, F3 x3, L1, L2 x4 in weight-row order)
+constexpr uint32_t k1rOnes = k1WBytes, k1rBias = k1rOnes + kOnesTile, k1rPart = kK1BiasMma ? k1rBias + 13 * kBiasBlock : k1WBytes;
+constexpr uint32_t k1rConst = k1rPart + 3 * 128 * 16, k1rBars = k1rConst + kc1Floats * 4, k1rSmem = k1rBars + 128;
+constexpr uint32_t k1rBiasF1 = k1rBias, k1rBiasF2 = k1rBias + kBiasBlock, k1rBiasF3 = k1rBias + 5 * kBiasBlock, k1rBiasL1 = k1rBias + 8 * kBiasBlock,
+                   k1rBiasL2 = k1rBias + 9 * kBiasBlock;
 static_assert(k1rSmem <= 232448, "exceeds 227 KB of shared memory");
 
-template <bool ISSUER>
+template <bool ISSUER, bool MULTI>
 __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s, WgCtx& cx, int me) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
   const Geometry& g = p.g;
-  const long ntiles = (p.q_end - p.q_begin + kTile - 1) / kTile;
+  const long ntiles = MULTI ? p.ntiles_total : (p.q_end - p.q_begin + kTile - 1) / kTile;
   const long stride = gridDim.x;
   const uint4* __restrict__ tab4 = reinterpret_cast<const uint4*>(p.tab);
   float4* part = reinterpret_cast<float4*>(smem + k1rPart) + me * 128;
@@ -1093,6 +1136,17 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
   uint64_t* slot_free = s.bars + 5;
   uint64_t* h2_read = s.bars + 7;
   constexpr int kStep = ISSUER ? 2 : 3;
+#ifdef STIF_DIAG_BIAS   // diagnostics (wrong results): 1 = bias MMAs AND epilogue adds, 2 = neither
+  constexpr bool NB = STIF_DIAG_BIAS == 1;
+#else
+  constexpr bool NB = !kK1BiasMma;   // epilogues add the bias themselves
+#endif
+  if constexpr (ISSUER) cx.ones_smem = wsm + k1rOnes;
+#if defined(STIF_DIAG_BIAS) && STIF_DIAG_BIAS == 2
+  auto bias_blocks = [&](uint32_t) {};
+#else
+  auto bias_blocks = [&](uint32_t off) { if constexpr (ISSUER && kK1BiasMma) cx.bias_smem = wsm + off; };
+#endif
   for (long n = me;; n += kStep) {
     const long tile = (long)blockIdx.x + n * stride;
     if (tile >= ntiles) break;
@@ -1104,7 +1158,10 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     cx.bar_base = 1 + 2 * slot;
     cx.n_steps = 0;
     cx.n_issued = cx.n_waited = 13u * seq;
-    const long q = p.q_begin + tile * kTile + cx.row;
+    long ltile = tile;
+    int sidx = 0;
+    if constexpr (MULTI) { sidx = (int)(tile / p.tiles_per_slab); ltile = tile - (long)sidx * p.tiles_per_slab; }
+    const long q = p.q_begin + ltile * kTile + cx.row;
     const bool valid = q < p.q_end;
     const long qc = valid ? q : p.q_end - 1;
     const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
@@ -1127,8 +1184,8 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int c = ch0 + j * 8 + e * 2;
-          const float b0 = fmaf(rely, p.c.a_rel[2 * c], fmaf(relx, p.c.a_rel[2 * c + 1], p.c.cA[c]));
-          const float b1 = fmaf(rely, p.c.a_rel[2 * c + 2], fmaf(relx, p.c.a_rel[2 * c + 3], p.c.cA[c + 1]));
+          const float b0 = fmaf(rely, p.c.a_rel[2 * c], fmaf(relx, p.c.a_rel[2 * c + 1], MULTI ? p.slab[sidx].cA[c] : p.c.cA[c]));
+          const float b1 = fmaf(rely, p.c.a_rel[2 * c + 2], fmaf(relx, p.c.a_rel[2 * c + 3], MULTI ? p.slab[sidx].cA[c + 1] : p.c.cA[c + 1]));
           pk[j * 4 + e] = pack_bf16x2(fast_sin(add_f16((uint16_t)(w4[e] & 0xFFFF), b0)), fast_sin(add_f16((uint16_t)(w4[e] >> 16), b1)));
         }
       }
@@ -1146,16 +1203,19 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     trace_mark(cx, 3);
 
     // ---- feat_imnet hidden layers (MMA phase on the slot from here on)
+    bias_blocks(k1rBiasF1);
     run_layer2<1, 4, false, ISSUER>(cx, cx.tmem + kColH0, wsm + k1F1, 64, [](int) { return 0; }, [&](int, int h, const uint32_t(&v)[16]) {
-      epi16_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.f1_b + ch0 + 16 * h);
+      epi16_sin_to_tmem<NB>(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.f1_b + ch0 + 16 * h);
     });
+    bias_blocks(k1rBiasF2);
     run_layer2<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1F2, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
-      epi16_sin_to_tmem(v, cx.lane_addr + kColA + 32 * i + CH * 16 + h * 8, p.c.f2_b + 64 * i + ch0 + 16 * h);
+      epi16_sin_to_tmem<NB>(v, cx.lane_addr + kColA + 32 * i + CH * 16 + h * 8, p.c.f2_b + 64 * i + ch0 + 16 * h);
     });
 
     // ---- composed last layer of feat_imnet: chunk order Q1, Q2, F
     auto f3_order = [](int i) { return i == 2 ? 0 : i + 1; };
     if constexpr (ISSUER) cx.extra_commit = &h2_read[slot];
+    bias_blocks(k1rBiasF3);
     layer_begin<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order);
     // ---- stage B gather: gB = bilinear(TB; query position) + cB + composed bias of F, kept as 32 fp16 values  (:410-418)
     uint32_t gBh[16];
@@ -1168,7 +1228,8 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
       for (int j = 0; j < 2; ++j) {
         float gB[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) gB[e] = p.c.cB[ch0 + 16 * j + e] + p.c.f3_b[ch0 + 16 * j + e];
+        for (int e = 0; e < 16; ++e)
+          gB[e] = (MULTI ? p.slab[sidx].cB[ch0 + 16 * j + e] : p.c.cB[ch0 + 16 * j + e]) + (NB ? p.c.f3_b[ch0 + 16 * j + e] : 0.f);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const U8x32 v = ldg256(tab4 + (long)tp.off[k] * 32 + 8 + CH * 4 + 2 * j);
@@ -1185,7 +1246,7 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     trace_mark(cx, 4);
     layer_finish2<3, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k1F3, 192, f3_order, [&](int i, int h, const uint32_t(&v)[16]) {
       if (i < 2) {
-        epi16_store_qtab(v, p.c.f3_b + 64 * (i + 1) + ch0 + 16 * h, p.qtab + qc * 128 + 64 * i + ch0 + 16 * h, valid);
+        epi16_store_qtab<NB>(v, p.c.f3_b + 64 * (i + 1) + ch0 + 16 * h, (MULTI ? p.slab[sidx].qtab : p.qtab) + qc * 128 + 64 * i + ch0 + 16 * h, valid);
       } else {   // f0 = sin(F + gB) -> bf16 -> TMEM
         uint32_t pk[8];
 #pragma unroll
@@ -1198,12 +1259,14 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     if constexpr (ISSUER) cx.extra_commit = nullptr;
 
     // ---- flow_imnet hidden layers; the 256->4 output layer rides the FMA pipe          (:419-422)
+    bias_blocks(k1rBiasL1);
     run_layer2<1, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L1, 64, [](int) { return 0; }, [&](int, int h, const uint32_t(&v)[16]) {
-      epi16_sin_to_tmem(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.l1_b + ch0 + 16 * h);
+      epi16_sin_to_tmem<NB>(v, cx.lane_addr + kColAin + CH * 16 + h * 8, p.c.l1_b + ch0 + 16 * h);
     });
     float2 fl[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    bias_blocks(k1rBiasL2);
     run_layer2<4, 4, false, ISSUER>(cx, cx.tmem + kColAin, wsm + k1L2, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
-      epi16_sin_fma<4>(v, p.c.l2_b + 64 * i + ch0 + 16 * h, cs + kc1L3W + 64 * i + ch0 + 16 * h, fl);
+      epi16_sin_fma<4, NB>(v, p.c.l2_b + 64 * i + ch0 + 16 * h, cs + kc1L3W + 64 * i + ch0 + 16 * h, fl);
     });
     if constexpr (ISSUER) {
       if ((threadIdx.x & 31) == 0) mbar_arrive(&slot_free[slot]);
@@ -1216,24 +1279,38 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
       STIF_BOUND(q, (long)g.HH * g.WW);
-      reinterpret_cast<float4*>(p.flow)[q] =
+      reinterpret_cast<float4*>(MULTI ? p.slab[sidx].flow : p.flow)[q] =
           make_float4(mine.x + o.x + p.c.l3_b[0], mine.y + o.y + p.c.l3_b[1], mine.z + o.z + p.c.l3_b[2], mine.w + o.w + p.c.l3_b[3]);
     }
   }
 }
 
+template <bool MULTI = false>
 __global__ void __launch_bounds__(832, 1) k1_stage_ab_rot_kernel(const __grid_constant__ K1Params p) {
   const CtaSetup s = cta_prologue(k1rBars, 0, p.wimg, k1WBytes, 512);
   {
     float* cs = reinterpret_cast<float*>(smem + k1rConst);
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) cs[kc1L3W + i] = p.c.l3_w[i];
+    if constexpr (kK1BiasMma) {   // 832 threads = 13 chunks x 64 bias rows; f1_b | f2_b | f3_b and l1_b | l2_b are contiguous in K1Consts
+      const int t = threadIdx.x;
+      const float b = t < 512 ? p.c.f1_b[t] : p.c.l1_b[t - 512];
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      uint8_t* row = smem + k1rBias + (t >> 6) * kBiasBlock;
+      *reinterpret_cast<uint4*>(row + nosw_offset(t & 63, 0)) = pack_bias_3term(b);
+      *reinterpret_cast<uint4*>(row + nosw_offset(t & 63, 8)) = zero;
+      if (t < 128) {
+        *reinterpret_cast<uint4*>(smem + k1rOnes + nosw_offset(t, 0)) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+        *reinterpret_cast<uint4*>(smem + k1rOnes + nosw_offset(t, 8)) = zero;
+      }
+      fence_proxy_async_smem();
+    }
     __syncthreads();
   }
   WgCtx cx = make_wg(s);
   if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (cx.issuer ? 24 + cx.wg : cx.slot) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
-  if (cx.issuer) k1_rot_loop<true>(p, s, cx, cx.wg);
-  else k1_rot_loop<false>(p, s, cx, cx.wg);
+  if (cx.issuer) k1_rot_loop<true, MULTI>(p, s, cx, cx.wg);
+  else k1_rot_loop<false, MULTI>(p, s, cx, cx.wg);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -1393,15 +1470,15 @@ __device__ __forceinline__ long k2_query(const K2Params& p, long tile, int r, bo
 __device__ __forceinline__ int tap_slot(int qi) { return (qi >> 2) * 32 + (qi & 3) * 6; }
 
 // phase 1 (bilinear footprints -> per-warp staging); issued one tile ahead, under the 256->256 layer's first MMA wait
-template <bool BAND>
-__device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile, int warp_in_wg, int lane) {
+template <bool BAND, bool MULTI = false>
+__device__ __forceinline__ void k2_gather_taps(const K2Params& p, uint4* stg, long tile, int warp_in_wg, int lane, int sidx = 0) {
   const Geometry& g = p.g;
   {
     const int qi = lane & 15, which = lane >> 4;
     bool valid_;
     int jy, jx;
     const long q = k2_query(p, tile, warp_in_wg * 16 + qi, valid_, jy, jx);
-    const float4 fl = __ldg(reinterpret_cast<const float4*>(p.flow) + q);
+    const float4 fl = __ldg(reinterpret_cast<const float4*>(MULTI ? p.slab[sidx].flow : p.flow) + q);
     float gy, gx;
     warp_position(g, jy, jx, which ? fl.z : fl.x, which ? fl.w : fl.y, gy, gx);   // (warplayer.py:25-39)
     Taps hr = make_taps(gy, gx, g.HH, g.WW);
@@ -1453,15 +1530,15 @@ __device__ __forceinline__ uint4 ldg128_hint(const uint4* p) {
 
 // phase 2 (loads + blend + sine -> A tile)
 // UADD (compile time: the hook costs registers the default kernel does not have): + p.uadd[q], decoding_test away from x4
-template <bool UADD = false, class Sig>
+template <bool UADD = false, bool MULTI = false, class Sig>
 __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, const uint4* stg, int warp_in_wg, int lane, Sig&& loads_issued,
-                                                long tile = 0) {
-  const char* __restrict__ qtab_b = reinterpret_cast<const char*>(p.qtab);
+                                                long tile = 0, int sidx = 0) {
+  const char* __restrict__ qtab_b = reinterpret_cast<const char*>(MULTI ? p.slab[sidx].qtab : p.qtab);
   const char* __restrict__ tab_b = reinterpret_cast<const char*>(p.tab);
   const int sub = lane & 7;
   float cE[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) cE[e] = p.c.cE[sub * 8 + e];
+  for (int e = 0; e < 8; ++e) cE[e] = MULTI ? p.slab[sidx].cE[sub * 8 + e] : p.c.cE[sub * 8 + e];
   // Software pipeline over 8 half-steps (4 queries x one warp position = 8 taps = 8 x 16 B per lane each): the loads
   // of half-step s+1 are in flight while half-step s is blended, so a warp exposes one memory round trip per tile
   // instead of four.  Step s: query group it = s/2, warp position which = s%2 (which 0 -> Q1/TE1 @ g1, 1 -> Q2/TE2 @ g2).
@@ -1535,17 +1612,20 @@ __device__ __forceinline__ void k2_gather_blend(const K2Params& p, uint8_t* a0, 
 
 // output stage: RGB of query q, either fp32 planar (the reference's tensor) or what its caller makes of it
 // (custom_video_test.py:102: `(img.clamp(0, 1) * 255).astype(uint8)` on the HWC frame -- fp32 clamp, fp32 multiply, truncation)
-__device__ __forceinline__ void k2_store_rgb(const K2Params& p, long q, float r, float g, float b) {
+template <bool MULTI = false>
+__device__ __forceinline__ void k2_store_rgb(const K2Params& p, long q, float r, float g, float b, int sidx = 0) {
   STIF_BOUND(q, p.plane);
-  if (p.out_u8) {
-    uint8_t* o = p.out_u8 + q * 3;
+  uint8_t* out_u8 = MULTI ? p.slab[sidx].out_u8 : p.out_u8;
+  float* out = MULTI ? p.slab[sidx].out : p.out;
+  if (out_u8) {
+    uint8_t* o = out_u8 + q * 3;
     o[0] = (uint8_t)(fminf(fmaxf(r, 0.f), 1.f) * 255.f);
     o[1] = (uint8_t)(fminf(fmaxf(g, 0.f), 1.f) * 255.f);
     o[2] = (uint8_t)(fminf(fmaxf(b, 0.f), 1.f) * 255.f);
   } else {
-    p.out[q] = r;
-    p.out[p.plane + q] = g;
-    p.out[2 * p.plane + q] = b;
+    out[q] = r;
+    out[p.plane + q] = g;
+    out[2 * p.plane + q] = b;
   }
 }
 
@@ -1649,13 +1729,13 @@ __global__ void __launch_bounds__(576, 1) k2_stage_cde_kernel(const __grid_const
 // the next tile's workgroup waits for that before its first arrival on the same named barriers.  Counters restart per
 // tile: 10 step barriers (even, so the id alternation restarts at 0) and 9 accumulator chunks per tile (the ring position
 // of tile k of a slot is 9 k).
-template <bool ISSUER, bool BAND, bool UADD>
+template <bool ISSUER, bool BAND, bool UADD, bool MULTI>
 __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s, WgCtx& cx, int me) {
   const int CH = cx.colhalf;
   const uint32_t wsm = smem_u32(smem);
   const int lane = threadIdx.x & 31, warp_in_wg = cx.warp_in_wg;
   const float* cs = reinterpret_cast<const float*>(smem + k2rConst);
-  const long ntiles = (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
+  const long ntiles = MULTI ? p.ntiles_total : (long)p.tiles_x * ((p.row_end - p.row_begin + 7) / 8);
   const long stride = gridDim.x;
   const int ch0 = CH * 32;
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, s.tmem_base, 0);
@@ -1664,9 +1744,16 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
   uint8_t* a0_mine = smem + k2A0 + me * 16384;                                    // (workgroups only)
   uint4* stg = reinterpret_cast<uint4*>(a0_mine + warp_in_wg * 2048);
   float4* part = reinterpret_cast<float4*>(smem + k2rPart) + me * 128;
+  auto slab_of = [&](long t, long& lt) {   // launch tile -> (slab, tile within the slab)
+    if constexpr (MULTI) { const int sx = (int)(t / p.tiles_per_slab); lt = t - (long)sx * p.tiles_per_slab; return sx; }
+    lt = t;
+    return 0;
+  };
   if constexpr (!ISSUER) {
     const long t0 = (long)blockIdx.x + (long)me * stride;
-    if (t0 < ntiles) k2_gather_taps<BAND>(p, stg, t0, warp_in_wg, lane);
+    long lt0;
+    const int s0 = slab_of(t0 < ntiles ? t0 : 0, lt0);
+    if (t0 < ntiles) k2_gather_taps<BAND, MULTI>(p, stg, lt0, warp_in_wg, lane, s0);
   }
   for (long n = me;; n += kStep) {
     const long tile = (long)blockIdx.x + n * stride;
@@ -1682,11 +1769,13 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     uint8_t* a0 = smem + k2A0 + wg * 16384;
     bool valid;
     int jy_, jx_;
-    const long q = k2_query(p, tile, cx.row, valid, jy_, jx_);
+    long ltile;
+    const int sidx = slab_of(tile, ltile);
+    const long q = k2_query(p, ltile, cx.row, valid, jy_, jx_);
     trace_mark(cx, 1);
     if constexpr (!ISSUER) {
       // ---- gather phase: no tensor memory, no named barrier of the slot                       (:424-456)
-      k2_gather_blend<UADD>(p, a0, stg, warp_in_wg, lane, []() {}, tile);
+      k2_gather_blend<UADD, MULTI>(p, a0, stg, warp_in_wg, lane, []() {}, ltile, sidx);
       fence_proxy_async_smem();
       tc_fence_before();
       trace_mark(cx, 2);
@@ -1706,7 +1795,11 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     layer_begin<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; });
     if constexpr (!ISSUER) {   // footprints of this workgroup's next tile, under the first 256->256 chunk's MMA time
       const long tile_next = tile + 3 * stride;
-      if (tile_next < ntiles) k2_gather_taps<BAND>(p, stg, tile_next, warp_in_wg, lane);
+      if (tile_next < ntiles) {
+        long ltn;
+        const int sn = slab_of(tile_next, ltn);
+        k2_gather_taps<BAND, MULTI>(p, stg, ltn, warp_in_wg, lane, sn);
+      }
     }
     layer_finish2<4, 16, false, ISSUER>(cx, cx.tmem + kColA, wsm + k2E3, 256, [](int i) { return i; }, [&](int i, int h, const uint32_t(&v)[16]) {
       epi16_sin_fma<3>(v, p.c.e3_b + 64 * i + ch0 + 16 * h, cs + kc2E4W + 64 * i + ch0 + 16 * h, rgb);
@@ -1721,13 +1814,13 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
     asm volatile("bar.sync %0, 256;" ::"r"(5 + me) : "memory");
     if (CH == 0 && valid) {
       const float4 o = part[cx.row];
-      k2_store_rgb(p, q, mine.x + o.x + p.c.e4_b[0], mine.y + o.y + p.c.e4_b[1], mine.z + o.z + p.c.e4_b[2]);
+      k2_store_rgb<MULTI>(p, q, mine.x + o.x + p.c.e4_b[0], mine.y + o.y + p.c.e4_b[1], mine.z + o.z + p.c.e4_b[2], sidx);
     }
     // (`part` is rewritten one whole tile later, after the workgroup has passed two of its own barriers)
   }
 }
 
-template <bool BAND, bool UADD = false>
+template <bool BAND, bool UADD = false, bool MULTI = false>
 __global__ void __launch_bounds__(832, 1) k2_stage_cde_rot_kernel(const __grid_constant__ K2Params p) {
   const CtaSetup s = cta_prologue(k2rBars, 0, p.wimg, k2WBytes, 512);
   {
@@ -1738,8 +1831,8 @@ __global__ void __launch_bounds__(832, 1) k2_stage_cde_rot_kernel(const __grid_c
   WgCtx cx = make_wg(s);   // warps 0, 1: issuers (cx.wg = TMEM slot); warps 2..25: workgroups 0..2
   if (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) cx.trace = p.trace + (cx.issuer ? 24 + cx.wg : cx.slot) * 4096;
   mbar_wait_or_trap(&s.bars[0], 0);
-  if (cx.issuer) k2_rot_loop<true, BAND, UADD>(p, s, cx, cx.wg);
-  else k2_rot_loop<false, BAND, UADD>(p, s, cx, cx.wg);
+  if (cx.issuer) k2_rot_loop<true, BAND, UADD, MULTI>(p, s, cx, cx.wg);
+  else k2_rot_loop<false, BAND, UADD, MULTI>(p, s, cx, cx.wg);
   cta_epilogue(s.tmem_base, 512);
 }
 
@@ -1816,7 +1909,10 @@ TcWeights* tc_weights_create(const FoldedWeights& hw, std::string& err) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2Smem);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_rot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_rot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_stage_ab_rot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k1rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k2_stage_cde_rot_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k2rSmem);
@@ -1945,7 +2041,7 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
     if (stage == 5 && !ws.utab) return cudaErrorInvalidValue;
 #if STIF_K1_ROT
     if (stage == 1) {
-      if (cudaError_t e = launch_pdl(k1_stage_ab_rot_kernel, (int)std::min<long>(cx.num_sms, ntiles), 832, k1rSmem, cx.stream, p)) return e;
+      if (cudaError_t e = launch_pdl(k1_stage_ab_rot_kernel<false>, (int)std::min<long>(cx.num_sms, ntiles), 832, k1rSmem, cx.stream, p)) return e;
       ++*cx.launch_counter;
       trace_dump("K1", cx.stream);
       return cudaGetLastError();
@@ -1999,6 +2095,72 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
 #endif
   ++*cx.launch_counter;
   trace_dump("K2", cx.stream);
+  return cudaGetLastError();
+}
+
+
+// The same stage of up to kMaxSlabs timesteps in ONE launch (band-major host pipeline): slab g has its own time t[g], tables
+// ws[g] and output; rows / band limits are shared.  stage 1 = K1 (stage A+B), stage 2 = K2 (stage C-E).
+cudaError_t decode_multi_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace* ws, const float* t, int nslab,
+                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* const* out_rgb, uint8_t* const* out_u8,
+                            int stage) {
+  if (nslab < 1 || nslab > kMaxSlabs) return cudaErrorInvalidValue;
+  const long WW = geo.WW;
+  if (stage == 1) {
+    K1Params p;
+    p.c = tw->c1;
+    p.g = geo;
+    p.tab = reinterpret_cast<const __half*>(ws[0].tab);
+    p.qtab = nullptr; p.flow = nullptr; p.ftab = nullptr; p.utab = nullptr;
+    p.wimg = tw->d_k1;
+    p.q_begin = k1_row_begin * WW;
+    p.q_end = k1_row_end * WW;
+    p.trace = nullptr;
+    p.tiles_per_slab = (p.q_end - p.q_begin + kTile - 1) / kTile;
+    p.ntiles_total = p.tiles_per_slab * nslab;
+    for (int g = 0; g < nslab; ++g) {
+      for (int c = 0; c < 64; ++c) {
+        p.slab[g].cA[c] = tw->a_t[c] * t[g] + tw->a_b[c];
+        p.slab[g].cB[c] = tw->b_t[c] * t[g] + tw->b_b[c];
+      }
+      p.slab[g].qtab = reinterpret_cast<__half*>(ws[g].qtab);
+      p.slab[g].flow = ws[g].flow;
+    }
+    if (cudaError_t e = launch_pdl(k1_stage_ab_rot_kernel<true>, (int)std::min<long>(cx.num_sms, p.ntiles_total), 832, k1rSmem, cx.stream, p)) return e;
+    ++*cx.launch_counter;
+    return cudaGetLastError();
+  }
+  K2Params p;
+  p.c = tw->c2;
+  p.g = geo;
+  p.tab = reinterpret_cast<const __half*>(ws[0].tab);
+  p.qtab = nullptr; p.flow = nullptr; p.out = nullptr; p.out_u8 = nullptr; p.uadd = nullptr;
+  p.plane = (long)geo.HH * geo.WW;
+  p.wimg = tw->d_k2;
+  p.row_begin = row_begin;
+  p.row_end = row_end;
+  p.col_begin = 0;
+  p.col_end = geo.WW;
+  p.tiles_x = (geo.WW + 15) / 16;
+  p.band_lo_off = k1_row_begin * geo.WW;
+  p.band_hi_off = k1_row_end * geo.WW;
+  p.flag = ws[0].flag;
+  p.trace = nullptr;
+  p.tiles_per_slab = (long)p.tiles_x * ((row_end - row_begin + 7) / 8);
+  p.ntiles_total = p.tiles_per_slab * nslab;
+  for (int g = 0; g < nslab; ++g) {
+    for (int c = 0; c < 64; ++c) p.slab[g].cE[c] = tw->e_t[c] * t[g] + tw->e_b[c];
+    p.slab[g].qtab = reinterpret_cast<const __half*>(ws[g].qtab);
+    p.slab[g].flow = ws[g].flow;
+    p.slab[g].out = out_rgb[g];
+    p.slab[g].out_u8 = out_u8 ? out_u8[g] : nullptr;
+  }
+  const int grid = (int)std::min<long>(cx.num_sms, p.ntiles_total);
+  const bool band = k1_row_begin > 0 || k1_row_end < geo.HH;
+  if (cudaError_t e = band ? launch_pdl(k2_stage_cde_rot_kernel<true, false, true>, grid, 832, k2rSmem, cx.stream, p)
+                           : launch_pdl(k2_stage_cde_rot_kernel<false, false, true>, grid, 832, k2rSmem, cx.stream, p))
+    return e;
+  ++*cx.launch_counter;
   return cudaGetLastError();
 }
 

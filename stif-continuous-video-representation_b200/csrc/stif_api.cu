@@ -334,10 +334,30 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
     cudaError_t e = cudaEventRecord(ev, from);
     return e != cudaSuccess ? e : cudaStreamWaitEvent(to, ev, 0);
   };
+  // STIF_HOST_MULTI=0: one launch per (band, timestep) as in round 1; default: the resident timesteps of a band share one K1 and
+  // one K2 launch (decode_multi_tc) -- half the launches of a T=2 call, and each launch's rotation fill / drain is paid once
+  static const bool multi = !(getenv("STIF_HOST_MULTI") && atoi(getenv("STIF_HOST_MULTI")) == 0);
+  static_assert(kHostGroup <= kMaxSlabsHost, "decode_multi_tc takes at most kMaxSlabsHost timesteps");
   // K2 of RGB rows [g0,g1) for timesteps [c0,c1) back to back (nothing between the launches, so each one's prologue
   // overlaps its predecessor's tail), then one event and the downloads of those rows
   auto k2_rows = [&](int b, int c0, int c1, bool resident, int g0, int g1, int k1_hi) -> int {
     if (g1 <= g0) return STIF_OK;
+    if (multi && resident && c1 - c0 > 1) {   // all resident timesteps of these rows in one launch
+      ScopedSpan sp(d, stream, 2);
+      Workspace wsv[kHostGroup];
+      float tv[kHostGroup];
+      float* ov[kHostGroup];
+      uint8_t* o8[kHostGroup];
+      for (int c = c0; c < c1; ++c) {
+        const size_t slab = ((size_t)c * B + b) * 3 * Q;
+        wsv[c - c0] = slab_ws(c);
+        tv[c - c0] = times[(size_t)c * B + b];
+        ov[c - c0] = out + slab;
+        o8[c - c0] = hp.out_u8_dev ? hp.out_u8_dev + slab : nullptr;
+      }
+      cudaError_t e = decode_multi_tc(cx, d->tcw, *geo, wsv, tv, c1 - c0, g0, g1, 0, k1_hi, ov, hp.out_u8_dev ? o8 : nullptr, 2);
+      if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+    } else
     for (int c = c0; c < c1; ++c) {
       ScopedSpan sp(d, stream, 2);
       const size_t slab = ((size_t)c * B + b) * 3 * Q;
@@ -402,6 +422,14 @@ int decode_host_banded(stif_decoder* d, const float* latent, const float* frames
       }
       mark(stream, "K0", b, k);
       const int h0 = k ? he[k - 1] : 0, h1 = he[k];
+      if (multi && G > 1 && h1 > h0) {
+        ScopedSpan sp(d, stream, 1);
+        Workspace wsv[kHostGroup];
+        float tv[kHostGroup];
+        for (int g = 0; g < G; ++g) { wsv[g] = slab_ws(g); tv[g] = times[(size_t)g * B + b]; }
+        cudaError_t e = decode_multi_tc(cx, d->tcw, *geo, wsv, tv, G, 0, HH, h0, h1, nullptr, nullptr, 1);
+        if (e != cudaSuccess) return set_error(STIF_ECUDA, "decode kernels failed: %s", cudaGetErrorString(e));
+      } else
       for (int g = 0; g < G && h1 > h0; ++g) {
         ScopedSpan sp(d, stream, 1);
         cudaError_t e = decode_slab_tc(cx, d->tcw, *geo, slab_ws(g), times[(size_t)g * B + b], 0, HH, h0, h1, out, 1);

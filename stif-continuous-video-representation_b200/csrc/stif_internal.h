@@ -133,6 +133,11 @@ cudaError_t decode_slab_tc(const LaunchCtx& cx, const TcWeights* tw, const Geome
 // decoding_test on the tensor-core kernels at sizes other than x4 (the upsampled-frame grid is then not the query grid):
 //   uq[HH*WW,192]  = UB bilinearly sampled at every query position | zeros  (per frame pair; k1_stage_ab_upf_kernel adds it)
 //   uadd[HH*WW,64] = bilinear(UE1; g1) + bilinear(UE2; g2) at the flow-warped positions of rows [row_begin,row_end) (per slab)
+constexpr int kMaxSlabsHost = 4;   // == kMaxSlabs of kernels_tc.cu
+// stage 1 (K1) or 2 (K2) of up to four timesteps in one launch (same rows, per-timestep tables ws[g] / outputs): band-major host pipeline
+cudaError_t decode_multi_tc(const LaunchCtx& cx, const TcWeights* tw, const Geometry& geo, const Workspace* ws, const float* t, int nslab,
+                            int row_begin, int row_end, int k1_row_begin, int k1_row_end, float* const* out_rgb, uint8_t* const* out_u8,
+                            int stage);
 cudaError_t resample_ub_tc(const LaunchCtx& cx, const void* utab, const Geometry& geo, void* uq);
 cudaError_t warp_u_terms_tc(const LaunchCtx& cx, const void* utab, const float* flow, const Geometry& geo, int row_begin, int row_end, void* uadd);
 cudaError_t project_frames_up4_tc(const LaunchCtx& cx, const TcWeights* tw, const float* frames6, int H, int W, void* utab);

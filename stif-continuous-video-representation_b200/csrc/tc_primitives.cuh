@@ -115,6 +115,20 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// K-major INTERLEAVED (no swizzle) operand of K = 16 bf16: 8 x 16-byte core matrices, the second K half LBO bytes on, the next
+// 8 rows SBO bytes on (cute UMMA canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units).  Used for the bias K step.
+constexpr uint32_t kNoswLBO = 128, kNoswSBO = 256;
+__host__ __device__ constexpr uint32_t nosw_offset(int r, int k) {
+  return (uint32_t)((r >> 3) * kNoswSBO + (k >> 3) * kNoswLBO + (r & 7) * 16 + (k & 7) * 2);
+}
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(kNoswLBO >> 4) << 16;
+  d |= (uint64_t)(kNoswSBO >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;   // layout type 0 = SWIZZLE_NONE
+}
 // Instruction descriptor for kind::f16 with bf16 A/B (K-major both), fp32 accumulate, M x N tile.
 //   bit 4: D fp32 | bits [7,10): A fmt (1 = bf16) | bits [10,13): B fmt | bits [17,23): N>>3 | bits [24,29): M>>4
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
@@ -198,6 +212,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2) and mixed-precision FMA (FHFMA: f16 * f16 + f32)
+// bias as two bf16 K entries (hi in the low half-word = k 0, lo = bias - hi in k 1): exact to ~2^-17 relative
+__device__ __forceinline__ uint32_t pack_bias_hi_lo(float b) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+// ... and with a third term the fp32 value exactly (3 x 8 mantissa bits): k 0..2 = hi, lo, lo2, k 3..7 = 0
+__device__ __forceinline__ uint4 pack_bias_3term(float b) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const float r1 = b - __bfloat162float(hi);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 lo2 = __float2bfloat16_rn(r1 - __bfloat162float(lo));
+  return make_uint4((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16), (uint32_t)__bfloat16_as_ushort(lo2), 0u, 0u);
+}
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
   unsigned long long r, x, y;
   asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a.x), "f"(a.y));

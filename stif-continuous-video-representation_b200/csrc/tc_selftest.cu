@@ -29,9 +29,12 @@ struct SelfTestParams {
   float* d1;          // [128,64]
   float* d2;          // [128,256]
   float* d3;          // [128,128]
+  const float* bias6; // [64] fp32
+  float* d6;          // [128,64]
   int* status;        // 0 = ok, else the step that timed out
 };
 
+constexpr uint32_t kOnesBytes = 128 * 32, kBiasBytes = 64 * 32;
 constexpr uint32_t kB1 = 64 * 128, kB2 = 256 * 128, kB3 = 4 * 128 * 128, kA1 = 128 * 128;
 
 __device__ bool wait_bounded(uint64_t* bar, uint32_t parity) {
@@ -49,6 +52,8 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(SelfTestParams p) {
   uint8_t* sB3 = sB2 + kB2;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sB3 + kB3);  // [0] load, [1] mma
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint8_t* sOnes = reinterpret_cast<uint8_t*>(bars) + 64;   // 128 x 16 bf16, interleaved (no swizzle): 4 KB
+  uint8_t* sBias = sOnes + kOnesBytes;                        // 64 x 16 bf16, interleaved: 2 KB
   const int tid = threadIdx.x, warp = tid >> 5;
 
   if (tid == 0) {
@@ -78,6 +83,16 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(SelfTestParams p) {
       v.z = pack_bf16x2(src[j * 8 + 4], src[j * 8 + 5]);
       v.w = pack_bf16x2(src[j * 8 + 6], src[j * 8 + 7]);
       *reinterpret_cast<uint4*>(sA1 + sw128_offset(tid, j * 8)) = v;
+    }
+  }
+  // T6 operands: A = [1, 1, 0 ...] per row, B row n = [bf16 hi(bias[n]), bf16 lo(bias[n]), 0 ...]
+  {
+    uint4 ones = make_uint4(0x3F803F80u, 0u, 0u, 0u), zero = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sOnes + nosw_offset(tid, 0)) = ones;
+    *reinterpret_cast<uint4*>(sOnes + nosw_offset(tid, 8)) = zero;
+    if (tid < 64) {
+      *reinterpret_cast<uint4*>(sBias + nosw_offset(tid, 0)) = make_uint4(pack_bias_hi_lo(p.bias6[tid]), 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(sBias + nosw_offset(tid, 8)) = zero;
     }
   }
   fence_proxy_async_smem();
@@ -156,6 +171,27 @@ __global__ void __launch_bounds__(128) tc_selftest_kernel(SelfTestParams p) {
       for (int j = 0; j < 32; ++j) p.d3[tid * 128 + c * 32 + j] = __uint_as_float(v[j]);
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  // ---------------- T6: TS K = 64 from A3's first 64 channels x B1, plus the bias as one extra K = 16 SS MMA (interleaved
+  // no-swizzle operands: a constant ones tile x a [hi, lo] bias block), D at columns [384, 448)
+  if (tid == 0) {
+    tc_fence_after();
+    uint64_t db = make_desc_sw128(smem_u32(sB1));
+    for (int k = 0; k < 4; ++k) umma_ts(tmem + 384, tmem + 8 * k, db + 2 * k, make_idesc_bf16(128, 64), k > 0);
+    umma_ss(tmem + 384, make_desc_nosw(smem_u32(sOnes)), make_desc_nosw(smem_u32(sBias)), make_idesc_bf16(128, 64), true);
+    umma_commit(&bars[1]);
+  }
+  if (!wait_bounded(&bars[1], 1)) { if (tid == 0) *p.status = 6; goto done; }
+  tc_fence_after();
+  {
+    uint32_t v[32];
+    for (int c = 0; c < 2; ++c) {
+      tmem_ld32(lane_base + 384 + c * 32, v);
+      tmem_ld_wait();
+      for (int j = 0; j < 32; ++j) p.d6[tid * 64 + c * 32 + j] = __uint_as_float(v[j]);
+    }
+  }
 done:
   tc_fence_before();
   __syncthreads();
@@ -217,10 +253,16 @@ int tc_selftest(int device, std::string& report) {
   for (auto& v : b1) v = bf16_round(rnd());
   for (auto& v : b2) v = bf16_round(rnd());
   for (auto& v : b3) v = bf16_round(rnd());
+  std::vector<float> bias6(64);
+  for (auto& v : bias6) v = 7.0f * rnd();
   auto i1 = pack_sw128(b1, 64, 64), i2 = pack_sw128(b2, 256, 64), i3 = pack_sw128(b3, 128, 256);
   uint8_t *db1, *db2, *db3;
   float *da1, *dd1, *dd2, *dd3;
   int* dstatus;
+  float *dbias6, *dd6;
+  cudaMalloc(&dbias6, 64 * 4); cudaMalloc(&dd6, 128 * 64 * 4);
+  cudaMemcpy(dbias6, bias6.data(), 64 * 4, cudaMemcpyHostToDevice);
+  cudaMemset(dd6, 0, 128 * 64 * 4);
   cudaMalloc(&db1, i1.size()); cudaMalloc(&db2, i2.size()); cudaMalloc(&db3, i3.size());
   cudaMalloc(&da1, a1.size() * 4); cudaMalloc(&dd1, 128 * 64 * 4); cudaMalloc(&dd2, 128 * 256 * 4);
   cudaMalloc(&dd3, 128 * 128 * 4); cudaMalloc(&dstatus, 4);
@@ -230,8 +272,8 @@ int tc_selftest(int device, std::string& report) {
   cudaMemcpy(da1, a1.data(), a1.size() * 4, cudaMemcpyHostToDevice);
   cudaMemset(dstatus, 0, 4);
   cudaMemset(dd1, 0, 128 * 64 * 4); cudaMemset(dd2, 0, 128 * 256 * 4); cudaMemset(dd3, 0, 128 * 128 * 4);
-  SelfTestParams p{db1, db2, db3, da1, dd1, dd2, dd3, dstatus};
-  size_t smem = kA1 + kB1 + kB2 + kB3 + 64 + 1024;
+  SelfTestParams p{db1, db2, db3, da1, dd1, dd2, dd3, dbias6, dd6, dstatus};
+  size_t smem = kA1 + kB1 + kB2 + kB3 + 64 + kOnesBytes + kBiasBytes + 1024;
   e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail("cudaFuncSetAttribute", e);
   tc_selftest_kernel<<<1, 128, smem>>>(p);
@@ -240,7 +282,9 @@ int tc_selftest(int device, std::string& report) {
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail("kernel", e);
   int status = 0;
-  std::vector<float> d1(128 * 64), d2(128 * 256), d3(128 * 128);
+  std::vector<float> d1(128 * 64), d2(128 * 256), d3(128 * 128), d6(128 * 64);
+  cudaMemcpy(d6.data(), dd6, d6.size() * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dbias6); cudaFree(dd6);
   cudaMemcpy(&status, dstatus, 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(d1.data(), dd1, d1.size() * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(d2.data(), dd2, d2.size() * 4, cudaMemcpyDeviceToHost);
@@ -276,12 +320,23 @@ int tc_selftest(int device, std::string& report) {
       for (int k = 0; k < 256; ++k) acc += (double)bf16_round(0.125f * d2[m * 256 + k]) * b3[n * 256 + k];
       r3[m * 128 + n] = (float)acc;
     }
+  std::vector<float> r6(128 * 64);
+  for (int m = 0; m < 128; ++m)
+    for (int n = 0; n < 64; ++n) {
+      double acc = bias6[n];
+      for (int k = 0; k < 64; ++k) acc += (double)bf16_round(0.125f * d2[m * 256 + k]) * b1[n * 64 + k];
+      r6[m * 64 + n] = (float)acc;
+    }
+  double m6;
+  const double e6 = compare(d6, r6, &m6);
   double m1, m2, m2s, m3;
   double e1 = compare(d1, r1, &m1), e2 = compare(d2, r2, &m2), e2s = compare(d2, r2swap, &m2s), e3 = compare(d3, r3, &m3);
   snprintf(line, sizeof line, "T1 SS  k64 n64 : max_abs_err %.3e (ref max %.3e)\n", e1, m1); report += line;
   snprintf(line, sizeof line, "T2 TS  k64 n256: max_abs_err %.3e (ref max %.3e) [swapped-halves hypothesis err %.3e]\n", e2, m2, e2s);
   report += line;
   snprintf(line, sizeof line, "T3 TS k256 n128: max_abs_err %.3e (ref max %.3e)\n", e3, m3); report += line;
+  snprintf(line, sizeof line, "T6 TS k64 n64 + bias as a K=16 no-swizzle SS MMA: max_abs_err %.3e (ref max %.3e)\n", e6, m6); report += line;
+  if (!(e6 < 2e-4 * std::max(1.0, m6))) rc = -1;
   snprintf(line, sizeof line, "samples D1[0][0..3] got %.5f %.5f %.5f %.5f ref %.5f %.5f %.5f %.5f\n", d1[0], d1[1], d1[2],
            d1[3], r1[0], r1[1], r1[2], r1[3]);
   report += line;
