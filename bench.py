@@ -394,7 +394,9 @@ def main_ours(args):
         if prof["count"][k]:
             per[name] = prof["ms"][k] / prof["count"][k]
     dom = max((n for n in per if not n.startswith("K0")), key=lambda n: per[n])
-    flop_launch = (FLOP_K1 if dom.startswith("K1") else FLOP_K2) * HH * WW
+    # queries one launch of the dominant kernel processes: the timesteps of a pair share launches (stif_workspace_bytes_grouped)
+    q_launch = args.steps * T * HH * WW / prof["count"][groups[dom]]
+    flop_launch = (FLOP_K1 if dom.startswith("K1") else FLOP_K2) * q_launch
     achieved = flop_launch / (per[dom] * 1e-3) / 1e12
     kernel_ms = sum(prof["ms"]) / args.steps
     traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (config 2 only)
@@ -402,10 +404,11 @@ def main_ours(args):
     if args.workload == "config2" and os.path.isfile(tpath):
         t = json.load(open(tpath)).get(dom)
         if t:
-            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
+            # the capture's launches cover t["queries_per_launch"] queries (one slab if absent); scale to this run's launches
+            traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) * q_launch / t.get("queries_per_launch", HH * WW)
     roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
             "frac": achieved / peak_burst, "peak_source": f"{peak_src} (burst; sustained {peak_sust})",
-            "traffic": traffic, "ms_per_launch": per[dom],
+            "traffic": traffic, "ms_per_launch": per[dom], "queries_per_launch": q_launch,
             "all_kernels_ms_per_launch": per,
             "share_of_step": {n: per[n] * prof["count"][groups[n]] / args.steps / kernel_ms for n in per},
             "whole_step_frac": qps / world * FLOP_PER_QUERY / 1e12 / peak_burst}
