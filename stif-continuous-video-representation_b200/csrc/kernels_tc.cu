@@ -1160,11 +1160,16 @@ __device__ __forceinline__ void k1_rot_loop(const K1Params& p, const CtaSetup& s
     cx.n_issued = cx.n_waited = 13u * seq;
     long ltile = tile;
     int sidx = 0;
-    if constexpr (MULTI) { sidx = (int)(tile / p.tiles_per_slab); ltile = tile - (long)sidx * p.tiles_per_slab; }
+    if constexpr (MULTI) {   // <= 4 slabs: compares instead of a 64-bit division
+      const long tps = p.tiles_per_slab;
+      sidx = (tile >= tps) + (tile >= 2 * tps) + (tile >= 3 * tps);
+      ltile = tile - (long)sidx * tps;
+    }
     const long q = p.q_begin + ltile * kTile + cx.row;
     const bool valid = q < p.q_end;
     const long qc = valid ? q : p.q_end - 1;
-    const int jy = (int)(qc / g.WW), jx = (int)(qc - (long)jy * g.WW);
+    // (rasters of this mode have at most 2^24 pixels, stif_api.cu: 32-bit division)
+    const int jy = (int)((uint32_t)qc / (uint32_t)g.WW), jx = (int)((uint32_t)qc - (uint32_t)jy * (uint32_t)g.WW);
     trace_mark(cx, 1);
     // ---- stage A, first layer (hoisted), WITHOUT the slot: h0 = sin(TA[iy,ix] + rel . w_rel + cA)      (:382-400)
     if constexpr (!ISSUER) {
@@ -1745,7 +1750,12 @@ __device__ __forceinline__ void k2_rot_loop(const K2Params& p, const CtaSetup& s
   uint4* stg = reinterpret_cast<uint4*>(a0_mine + warp_in_wg * 2048);
   float4* part = reinterpret_cast<float4*>(smem + k2rPart) + me * 128;
   auto slab_of = [&](long t, long& lt) {   // launch tile -> (slab, tile within the slab)
-    if constexpr (MULTI) { const int sx = (int)(t / p.tiles_per_slab); lt = t - (long)sx * p.tiles_per_slab; return sx; }
+    if constexpr (MULTI) {   // <= 4 slabs: compares instead of a 64-bit division
+      const long tps = p.tiles_per_slab;
+      const int sx = (t >= tps) + (t >= 2 * tps) + (t >= 3 * tps);
+      lt = t - (long)sx * tps;
+      return sx;
+    }
     lt = t;
     return 0;
   };
