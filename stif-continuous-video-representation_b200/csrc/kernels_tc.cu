@@ -442,6 +442,15 @@ __device__ __forceinline__ void run_layer(WgCtx& cx, uint32_t a_base, uint32_t w
 // which of a thread's 16 sine pairs go to the FMA-pipe polynomial (evenly interleaved with the MUFU ones)
 __host__ __device__ constexpr bool use_poly(int j) { return ((j * kPolyPairs) % 16) < kPolyPairs; }
 
+// rotation kernels: of the 8 sine pairs of a 16-column half-chunk, KPOLY16 run on the FMA pipe (poly_sin2), spread evenly
+#ifndef KPOLY16
+#define KPOLY16 0
+#endif
+__host__ __device__ constexpr bool use_poly16(int jp) { return ((jp * KPOLY16) % 8) < KPOLY16; }
+__device__ __forceinline__ float2 sin2_mixed(float2 a, int jp) {
+  if (use_poly16(jp)) return poly_sin2(a);
+  return make_float2(fast_sin(a.x), fast_sin(a.y));
+}
 // 4 consecutive constants in one 128-bit constant-bank load (all bias / weight arrays are 16-byte aligned at 4-element steps)
 __device__ __forceinline__ float4 ldc4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
@@ -647,8 +656,9 @@ __device__ __forceinline__ void epi16_sin_to_tmem(const uint32_t (&v)[16], uint3
     const float4 b4 = ldc4(bias + 4 * j4);
     const float2 a0 = add2(make_float2(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1])), make_float2(b4.x, b4.y));
     const float2 a1 = add2(make_float2(__uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3])), make_float2(b4.z, b4.w));
-    pk[2 * j4] = pack_bf16x2(fast_sin(a0.x), fast_sin(a0.y));
-    pk[2 * j4 + 1] = pack_bf16x2(fast_sin(a1.x), fast_sin(a1.y));
+    const float2 s0 = sin2_mixed(a0, 2 * j4), s1 = sin2_mixed(a1, 2 * j4 + 1);
+    pk[2 * j4] = pack_bf16x2(s0.x, s0.y);
+    pk[2 * j4 + 1] = pack_bf16x2(s1.x, s1.y);
   }
   tmem_st8(dst, pk);
 }
@@ -670,8 +680,7 @@ __device__ __forceinline__ void epi16_sin_fma(const uint32_t (&v)[16], const flo
     for (int h = 0; h < 2; ++h) {
       float2 s = make_float2(__uint_as_float(v[4 * j4 + 2 * h]), __uint_as_float(v[4 * j4 + 2 * h + 1]));
       if constexpr (BIAS) s = add2(s, h ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
-      s.x = fast_sin(s.x);
-      s.y = fast_sin(s.y);
+      s = sin2_mixed(s, 2 * j4 + h);
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) acc[k] = fma2(s, h ? make_float2(w4[k].z, w4[k].w) : make_float2(w4[k].x, w4[k].y), acc[k]);
     }
