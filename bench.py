@@ -178,7 +178,7 @@ def main_reference(args):
                              "sample": res["sample"], "source": res["source"]},
             "e2e": {"value": res["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_subprocess(sample: str, steps: int):
@@ -434,12 +434,29 @@ def main_ours(args):
             "output_checksum": checksum}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_subprocess(args.cpu_sample if args.cpu_sample != "quarter" else "full", args.cpu_steps)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE line of this run's stdout (libraries that chat on fd 1 -- NCCL's version banner -- were sent to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)      # keep the real stdout for the result line ...
+    os.dup2(2, 1)               # ... and point fd 1 at stderr for everything else in this process and its libraries
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
