@@ -179,7 +179,9 @@ int stif_decode_host_bf16(stif_decoder_t* dec,
  *   tap k), mask [B, dg*kh*kw, H, W], out [B,Cout,H,W]; stream-ordered on `stream`.
  * Implemented: the one geometry the reference's encoder uses (C = Cout = 64, 3x3, stride 1, padding 1, dilation 1, dg = 8;
  * Sakuya_arch_test.py:38-66,135-160) as a fused deformable-im2col + tcgen05 kernel with a 2-term bf16 operand split
- * (fp32-class accuracy).  Any other geometry returns STIF_EINVAL without touching `out`: the caller keeps its fallback. */
+ * (fp32-class accuracy).  Any other geometry returns STIF_EINVAL without touching `out`: the caller keeps its fallback.
+ * No decoder handle and no state of the caller's: the channels-last copy of the input the kernel gathers from is a stream-ordered
+ * allocation from a per-device pool the library owns, so calls on different streams / threads are independent. */
 int stif_dcn_v2_forward(const float* input_dev, const float* weight_dev, const float* bias_dev,
                         const float* offset_dev, const float* mask_dev,
                         int B, int C, int H, int W, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,

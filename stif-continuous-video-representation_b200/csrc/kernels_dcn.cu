@@ -12,6 +12,7 @@
 // [64 x 64] weight block by tcgen05.mma, nine taps accumulating into one fp32 TMEM accumulator.  fp32-class accuracy comes
 // from the same 2-term bf16 split as the high-precision decoder mode (kernels_hp.cu): a_hi w_hi + a_lo w_hi + a_hi w_lo.
 #include <algorithm>
+#include <mutex>
 #include <cstdio>
 #include <string>
 
@@ -186,9 +187,12 @@ __global__ void dcn_pack_input_kernel(const float* __restrict__ in, float* __res
   stg256(out + i * 8, v);
 }
 
-// scratch for the packed input, one per device, grown on demand (the only state of this entry point)
-struct DcnScratch { float* buf = nullptr; size_t bytes = 0; };
-DcnScratch g_dcn_scratch[64];
+// cudaFuncSetAttribute is per device: remember where the kernel's shared-memory limit has been raised
+// ... and keep one stream-ordered memory pool per device for the packed input (release threshold = never: after the first call an
+// allocation is a pool hit, a few microseconds; the device's default pool would hand its memory back at every synchronisation)
+std::mutex g_dcn_mutex;
+bool g_dcn_configured[64] = {};
+cudaMemPool_t g_dcn_pool[64] = {};
 
 }  // namespace
 }  // namespace stif
@@ -200,27 +204,33 @@ extern "C" int stif_dcn_v2_forward(const float* input, const float* weight, cons
   if (!input || !weight || !bias || !offset || !mask || !out || B < 1 || H < 1 || W < 1) return STIF_EINVAL;
   if (C != 64 || Cout != 64 || kh != 3 || kw != 3 || sh != 1 || sw != 1 || ph != 1 || pw != 1 || dh != 1 || dw != 1 || dg != 8)
     return STIF_EINVAL;   // not the encoder's configuration: the caller keeps its own path
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(dcn_v2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dSmem) != cudaSuccess) return STIF_ECUDA;
-    configured = true;
-  }
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STIF_ECUDA;
-  const long ntiles = ((long)B * H * W + 127) / 128;
   if (dev < 0 || dev >= 64) return STIF_EINVAL;
-  DcnScratch& sc = g_dcn_scratch[dev];
-  const size_t need = (size_t)B * 64 * H * W * sizeof(float);
-  if (sc.bytes < need) {
-    if (sc.buf) cudaFree(sc.buf);
-    sc.buf = nullptr;
-    sc.bytes = 0;
-    if (cudaMalloc(&sc.buf, need) != cudaSuccess) return STIF_ECUDA;
-    sc.bytes = need;
+  {
+    std::lock_guard<std::mutex> lock(g_dcn_mutex);
+    if (!g_dcn_configured[dev]) {
+      if (cudaFuncSetAttribute(dcn_v2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dSmem) != cudaSuccess) return STIF_ECUDA;
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if (cudaMemPoolCreate(&g_dcn_pool[dev], &props) != cudaSuccess) return STIF_ECUDA;
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(g_dcn_pool[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+      g_dcn_configured[dev] = true;
+    }
   }
+  const long ntiles = ((long)B * H * W + 127) / 128;
+  // packed copy of the input: stream-ordered allocation (the pool recycles it), so the entry point keeps no buffer of its own and
+  // concurrent calls on different streams do not share one
+  float* packed = nullptr;
+  if (cudaMallocFromPoolAsync(&packed, (size_t)B * 64 * H * W * sizeof(float), g_dcn_pool[dev], (cudaStream_t)stream) != cudaSuccess) return STIF_ECUDA;
   const long npack = (long)B * 8 * H * W;
-  dcn_pack_input_kernel<<<(unsigned)((npack + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, sc.buf, (long)H * W, npack);
-  DcnParams p{sc.buf, weight, bias, offset, mask, out, B, H, W};
+  dcn_pack_input_kernel<<<(unsigned)((npack + 255) / 256), 256, 0, (cudaStream_t)stream>>>(input, packed, (long)H * W, npack);
+  DcnParams p{packed, weight, bias, offset, mask, out, B, H, W};
   dcn_v2_forward_kernel<<<(unsigned)std::min<long>(sms, ntiles), 512, dSmem, (cudaStream_t)stream>>>(p);
-  return cudaGetLastError() == cudaSuccess ? STIF_OK : STIF_ECUDA;
+  const cudaError_t e = cudaGetLastError();
+  const cudaError_t ef = cudaFreeAsync(packed, (cudaStream_t)stream);
+  return e == cudaSuccess && ef == cudaSuccess ? STIF_OK : STIF_ECUDA;
 }
