@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,15 @@ struct HpGemmParams {
 };
 
 extern __shared__ __align__(1024) uint8_t hp_smem[];
+
+// STIF_HP_SINF=1 at build time keeps libdevice's sinf in the epilogues (the accuracy anchor of reduced_sin)
+__device__ __forceinline__ float hp_sin(float x) {
+#ifdef STIF_HP_SINF
+  return sinf(x);
+#else
+  return reduced_sin(x);
+#endif
+}
 
 __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(256, K == 64 ? 2 : 1) hp_gemm_kernel(const __g
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
-      o[j] = p.act ? sinf(x) : x;
+      o[j] = p.act ? hp_sin(x) : x;
     }
     if (row < p.M) {
       float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + col0);
@@ -139,6 +149,142 @@ __global__ void __launch_bounds__(256, K == 64 ? 2 : 1) hp_gemm_kernel(const __g
   if (warp == 0) tmem_dealloc(tmem, 128);
 }
 
+
+// ---- version 2: persistent, pipelined over K blocks and tiles ----------------------------------------------------------------
+// Version 1 above is one 128-row tile per CTA with everything in sequence (A load -> split -> per chunk: weight TMA -> MMAs ->
+// epilogue): 1.4 TB/s of HBM traffic where the layers need ~5.  Here a CTA is persistent and has three roles:
+//   warps 8-15  producers (one group of four warps per stage of a 2-deep ring): the next 64-wide K block of A (fp32 -> hi / lo
+//               SW128 tiles) and, by bulk TMA, the layer's weight rows for that K block (hi and lo, all N columns);
+//   warp 16     issuer: 3 x 4 x N/64 MMAs per stage into the tile's N accumulator columns, tcgen05.commit frees the stage;
+//   warps 0-7   epilogue of the PREVIOUS tile from the other half of TMEM (2 x 256 columns): bias, sine, fp32 rows.
+// so loads, tensor work and the sine / store epilogue of neighbouring tiles overlap.  Same arithmetic as version 1 (same three
+// terms, same order within an accumulator), so the two agree bit for bit.
+constexpr uint32_t kHp2StageA = 2 * 16384;   // A hi | A lo of one K block
+__host__ __device__ constexpr uint32_t hp2_stage_bytes(int N) { return kHp2StageA + 2u * (uint32_t)N * 128u; }
+__host__ __device__ constexpr uint32_t hp2_smem_bytes(int N) { return 2u * hp2_stage_bytes(N) + 128u; }
+
+__global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant__ HpGemmParams p) {
+  const int KB = p.K / 64, NC = p.N / 64;
+  const uint32_t stage_bytes = hp2_stage_bytes(p.N), w_bytes = (uint32_t)p.N * 128u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hp_smem + 2 * stage_bytes);   // [0,1] stage full, [2,3] stage empty, [4,5] accumulator full, [6,7] accumulator empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars[s], 129);       // 128 producer threads + the expect_tx arrival of the weight TMA
+      mbar_init(&bars[2 + s], 1);     // tcgen05.commit
+      mbar_init(&bars[4 + s], 1);     // tcgen05.commit
+      mbar_init(&bars[6 + s], 256);   // the epilogue threads
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long ntiles = (p.M + 127) / 128;
+  if (warp < 8) {
+    // ---------------- epilogue: thread = one row x half of the N columns
+    const int quarter = warp & 3, ncol = p.N / 2, cbeg = (warp >> 2) * ncol;
+    long it = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const uint32_t b = (uint32_t)(it & 1);
+      wait_or_trap(&bars[4 + b], (uint32_t)(it >> 1) & 1);
+      tc_fence_after();
+      const long row = tile * 128 + quarter * 32 + lane;
+      for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256u + (uint32_t)c0, v);
+        tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
+          o[j] = p.act ? hp_sin(x) : x;
+        }
+        if (row < p.M) {
+          float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars[6 + b]);
+    }
+  } else if (warp < 16) {
+    // ---------------- producers: group 0 (warps 8-11) fills stage 0 with the even items, group 1 (warps 12-15) stage 1 with the
+    // odd ones, so that two stages' worth of loads (64 KB per SM) are in flight
+    const int pt = (tid - 256) & 127;
+    const uint32_t group = (uint32_t)(tid - 256) >> 7;
+    long item = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+      for (int kb = 0; kb < KB; ++kb, ++item) {
+        const uint32_t s = (uint32_t)(item & 1);
+        if (s != group) continue;
+        wait_or_trap(&bars[2 + s], ((uint32_t)(item >> 1) & 1) ^ 1);   // (passes at once the first time round)
+        uint8_t* st = hp_smem + s * stage_bytes;
+        if (pt == 0) {
+          mbar_arrive_expect_tx(&bars[s], 2 * w_bytes);
+          const size_t off = ((size_t)kb * p.n_total + p.n_off) * 128;
+          bulk_copy_g2s(st + kHp2StageA, p.w_hi + off, w_bytes, &bars[s]);
+          bulk_copy_g2s(st + kHp2StageA + w_bytes, p.w_lo + off, w_bytes, &bars[s]);
+        }
+        float4 v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int idx = pt + 128 * i, row = idx >> 4, k = (idx & 15) * 4;
+          const long m = tile * 128 + row;
+          v[i] = m < p.M ? __ldg(reinterpret_cast<const float4*>(p.A + m * p.K + kb * 64 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int idx = pt + 128 * i, row = idx >> 4, k = (idx & 15) * 4;
+          const uint32_t h0 = pack_bf16x2(v[i].x, v[i].y), h1 = pack_bf16x2(v[i].z, v[i].w);
+          const float r0 = v[i].x - __uint_as_float(h0 << 16), r1 = v[i].y - __uint_as_float(h0 & 0xFFFF0000u);
+          const float r2 = v[i].z - __uint_as_float(h1 << 16), r3 = v[i].w - __uint_as_float(h1 & 0xFFFF0000u);
+          const uint32_t off = sw128_offset(row, k);
+          *reinterpret_cast<uint2*>(st + off) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(st + 16384 + off) = make_uint2(pack_bf16x2(r0, r1), pack_bf16x2(r2, r3));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars[s]);
+      }
+  } else if (lane == 0) {
+    // ---------------- issuer
+    const uint32_t idesc = make_idesc_bf16(128, 64);
+    long item = 0, it = 0;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const uint32_t b = (uint32_t)(it & 1);
+      wait_or_trap(&bars[6 + b], ((uint32_t)(it >> 1) & 1) ^ 1);       // the epilogue has drained this half of TMEM
+      tc_fence_after();
+      for (int kb = 0; kb < KB; ++kb, ++item) {
+        const uint32_t s = (uint32_t)(item & 1);
+        wait_or_trap(&bars[s], (uint32_t)(item >> 1) & 1);
+        tc_fence_after();
+        const uint32_t ah = smem_u32(hp_smem + s * stage_bytes), al = ah + 16384, wh = ah + kHp2StageA, wl = wh + w_bytes;
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t d = tmem + b * 256u + (uint32_t)c * 64u;
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {                       // a_hi w_hi, a_lo w_hi, a_hi w_lo
+            const uint32_t a = term == 1 ? al : ah, w = (term == 2 ? wl : wh) + (uint32_t)c * 8192u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_ss(d, make_desc_sw128(a) + 2 * j, make_desc_sw128(w) + 2 * j, idesc, kb > 0 || term > 0 || j > 0);
+          }
+        }
+        umma_commit(&bars[2 + s]);
+      }
+      umma_commit(&bars[4 + b]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 template <int K>
 constexpr size_t hp_smem_bytes() { return 2 * (size_t)(K / 64) * 16384 + 2 * (size_t)(K / 64) * 8192 + 64; }
 
@@ -180,6 +326,7 @@ HpWeights* hp_weights_create(const FoldedWeights& hw, std::string& err) {
   }
   cudaError_t e = cudaFuncSetAttribute(hp_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<64>());
   if (e == cudaSuccess) e = cudaFuncSetAttribute(hp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<256>());
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp2_smem_bytes(256));
   if (e != cudaSuccess) {
     err = cudaGetErrorString(e);
     hp_weights_destroy(t);
@@ -203,6 +350,12 @@ cudaError_t hp_gemm(const LaunchCtx& cx, const HpLayer& L, int n_off, int N, con
   if (N % 64 != 0 || n_off % 8 != 0 || n_off + N > L.N || (L.K != 64 && L.K != 256) || ldc % 4 != 0) return cudaErrorInvalidValue;
   HpGemmParams p{A, L.hi, L.lo, bias, C, ldc, M, L.N, n_off, N, L.K, act};
   const unsigned grid = (unsigned)((M + 127) / 128);
+  static const bool v1 = getenv("STIF_HP_V1") && atoi(getenv("STIF_HP_V1")) != 0;   // A/B switch: the one-tile-per-CTA kernel
+  if (!v1 && N <= 256) {
+    hp_gemm2_kernel<<<std::min<unsigned>(grid, (unsigned)cx.num_sms), 544, hp2_smem_bytes(N), cx.stream>>>(p);
+    ++*cx.launch_counter;
+    return cudaGetLastError();
+  }
   if (L.K == 64) hp_gemm_kernel<64><<<grid, 256, hp_smem_bytes<64>(), cx.stream>>>(p);
   else hp_gemm_kernel<256><<<grid, 256, hp_smem_bytes<256>(), cx.stream>>>(p);
   ++*cx.launch_counter;
@@ -231,6 +384,7 @@ int hp_selftest(std::string& report) {
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice); cudaMemcpy(dB, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(hp_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<64>());
     cudaFuncSetAttribute(hp_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp_smem_bytes<256>());
+    cudaFuncSetAttribute(hp_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hp2_smem_bytes(256));
     int64_t launches = 0;
     LaunchCtx cx{nullptr, &launches, 148};
     cudaError_t e = hp_gemm(cx, L, 64, N, dA, dB, dC, N, M, 0);       // outputs 64..191 of the layer
