@@ -11,6 +11,7 @@
 #include <cstdio>
 
 #include "stif_internal.h"
+#include "tc_primitives.cuh"
 
 namespace stif {
 namespace {
@@ -157,18 +158,33 @@ struct Vec64 { float v[64]; };
 
 // Stage A first layer (hoisted): h0 = sin(TA[iy,ix] + rel_y*w_ry + rel_x*w_rx + (w_t t + b))
 // reference: Sakuya_arch_test.py:382-400 (nearest gathers, rel_coord, pe_coord, first SineLayer).
+// (first-layer kernels: thread = (query, 4 consecutive channels) -- 16 threads share a query's index / tap arithmetic instead of
+// 64, every table access is one 16-byte load; the sine is tc::reduced_sin as in the dense layers' epilogues)
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float w, const float4 v, float4& s) {
+  s.x = fmaf(w, v.x, s.x); s.y = fmaf(w, v.y, s.y); s.z = fmaf(w, v.z, s.z); s.w = fmaf(w, v.w, s.w);
+}
+__device__ __forceinline__ float4 sin4(const float4 v) {
+  return make_float4(tc::reduced_sin(v.x), tc::reduced_sin(v.y), tc::reduced_sin(v.z), tc::reduced_sin(v.w));
+}
 __global__ void stage_a_first_layer(const float* __restrict__ tab, Geometry g, const float* __restrict__ a_rel, Vec64 cst,
                                     long q0, long n, float* __restrict__ out) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * 64) return;
-  int c = (int)(i & 63);
-  long q = q0 + (i >> 6);
+  if (i >= n * 16) return;
+  int c = (int)(i & 15) * 4;
+  long q = q0 + (i >> 4);
   int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
   int iy = g.y.idx[jy], ix = g.x.idx[jx];
-  float ta = 0.f;
-  if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) ta = tab[((long)iy * g.W + ix) * 256 + c];
-  float v = ta + g.y.rel[jy] * a_rel[c * 2 + 0] + g.x.rel[jx] * a_rel[c * 2 + 1] + cst.v[c];
-  out[i] = sinf(v);
+  float4 ta = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) ta = ld4(tab + ((long)iy * g.W + ix) * 256 + c);
+  const float ry = g.y.rel[jy], rx = g.x.rel[jx];
+  const float4 r0 = ld4(a_rel + c * 2), r1 = ld4(a_rel + c * 2 + 4);   // [c][2]: (w_ry, w_rx) pairs
+  float4 v;
+  v.x = ta.x + ry * r0.x + rx * r0.y + cst.v[c];
+  v.y = ta.y + ry * r0.z + rx * r0.w + cst.v[c + 1];
+  v.z = ta.z + ry * r1.x + rx * r1.y + cst.v[c + 2];
+  v.w = ta.w + ry * r1.z + rx * r1.w + cst.v[c + 3];
+  reinterpret_cast<float4*>(out)[i] = sin4(v);
 }
 
 // Stage B first layer (hoisted): f0 = sin(F + bilinear(TB; query position) + (w_t t + b))
@@ -186,25 +202,26 @@ __global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, V
                                     float* __restrict__ f_inout, const float* __restrict__ f_table,
                                     const float* __restrict__ utab) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * 64) return;
-  int c = (int)(i & 63);
-  long q = q0 + (i >> 6);
+  if (i >= n * 16) return;
+  int c = (int)(i & 15) * 4;
+  long q = q0 + (i >> 4);
   int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
   Taps tp = make_taps_tables(g, jy, jx);
-  float s = 0.f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) s = fmaf(tp.w[k], tab[(long)tp.off[k] * 256 + 64 + c], s);
+  for (int k = 0; k < 4; ++k) fma4(tp.w[k], ld4(tab + (long)tp.off[k] * 256 + 64 + c), s);
   if (utab) {   // decoding_test: frames sampled bilinearly from the x4-upsampled pair at the query position (:520-523)
     const Taps up = make_taps(query_coord(jy, g.HH), query_coord(jx, g.WW), 4 * g.H, 4 * g.W);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s = fmaf(up.w[k], utab[(long)up.off[k] * 192 + c], s);
+    for (int k = 0; k < 4; ++k) fma4(up.w[k], ld4(utab + (long)up.off[k] * 192 + c), s);
   }
-  float f = f_inout[i];
+  float4 f = reinterpret_cast<float4*>(f_inout)[i];
   if (f_table) {
     const int hy = g.y.hidx[jy], hx = g.x.hidx[jx];
-    f = (hy >= 0 && hy < g.HH && hx >= 0 && hx < g.WW) ? f_table[((long)hy * g.WW + hx) * 64 + c] : 0.f;
+    f = (hy >= 0 && hy < g.HH && hx >= 0 && hx < g.WW) ? ld4(f_table + ((long)hy * g.WW + hx) * 64 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  f_inout[i] = sinf(f + s + cst.v[c]);
+  reinterpret_cast<float4*>(f_inout)[i] =
+      sin4(make_float4(f.x + s.x + cst.v[c], f.y + s.y + cst.v[c + 1], f.z + s.z + cst.v[c + 2], f.w + s.w + cst.v[c + 3]));
 }
 
 // ret = ret + pred_k * (area_{3-k} / tot_area), every operation separately rounded as the reference's ATen kernels do
@@ -235,12 +252,12 @@ __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* 
                                     int band_lo, int band_hi, int* __restrict__ flag, float* __restrict__ out,
                                     const float* __restrict__ utab) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * 64) return;
-  int c = (int)(i & 63);
-  long q = q0 + (i >> 6);
+  if (i >= n * 16) return;
+  int c = (int)(i & 15) * 4;
+  long q = q0 + (i >> 4);
   int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
   float4 fl = reinterpret_cast<const float4*>(flow)[q];
-  float s = cst.v[c];
+  float4 s = make_float4(cst.v[c], cst.v[c + 1], cst.v[c + 2], cst.v[c + 3]);
 #pragma unroll
   for (int wv = 0; wv < 2; ++wv) {
     float gy, gx;
@@ -255,17 +272,17 @@ __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* 
       if (hr.w[k] == 0.f) continue;
       const int row = hr.off[k] / g.WW;
       if (row < band_lo || row >= band_hi) { if (c == 0) atomicOr(flag, 1); continue; }
-      s = fmaf(hr.w[k], qtab[(long)hr.off[k] * 128 + wv * 64 + c], s);
+      fma4(hr.w[k], ld4(qtab + (long)hr.off[k] * 128 + wv * 64 + c), s);
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) s = fmaf(lr.w[k], tab[(long)lr.off[k] * 256 + 128 + wv * 64 + c], s);
+    for (int k = 0; k < 4; ++k) fma4(lr.w[k], ld4(tab + (long)lr.off[k] * 256 + 128 + wv * 64 + c), s);
     if (utab) {   // decoding_test: frames at the warped position come from the x4-upsampled pair (:548-551, :562-565)
       const Taps up = make_taps(gy, gx, 4 * g.H, 4 * g.W);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s = fmaf(up.w[k], utab[(long)up.off[k] * 192 + 64 + wv * 64 + c], s);
+      for (int k = 0; k < 4; ++k) fma4(up.w[k], ld4(utab + (long)up.off[k] * 192 + 64 + wv * 64 + c), s);
     }
   }
-  out[i] = sinf(s);
+  reinterpret_cast<float4*>(out)[i] = sin4(s);
 }
 
 Vec64 time_constant(const std::vector<float>& wt, const std::vector<float>& b, float t) {
@@ -457,7 +474,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
   // ---- K1: stage A + B over rows [k1_row_begin, k1_row_end)
   for (long q0 = k1_row_begin * WW; stage == 1 && q0 < k1_row_end * WW; q0 += chunk) {
     long n = std::min(chunk, k1_row_end * WW - q0);
-    unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+    unsigned blocks = (unsigned)((n * 16 + 255) / 256);
     stage_a_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, w.a_rel, cA, q0, n, ws.act_c);
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
@@ -475,7 +492,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
   // ---- K2: stage C + D + E over rows [row_begin, row_end)
   for (long q0 = row_begin * WW; stage == 2 && q0 < row_end * WW; q0 += chunk) {
     long n = std::min(chunk, row_end * WW - q0);
-    unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+    unsigned blocks = (unsigned)((n * 16 + 255) / 256);
     stage_e_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end,
                                                       ws.flag, ws.act_c, reinterpret_cast<const float*>(ws.utab));
     ++*cx.launch_counter;
@@ -510,7 +527,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
     // stage A for the whole slab: F and Q tables (stage B gathers F at OTHER pixels in this mode)
     for (long q0 = 0; q0 < Q; q0 += chunk) {
       long n = std::min(chunk, Q - q0);
-      unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+      unsigned blocks = (unsigned)((n * 16 + 255) / 256);
       stage_a_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, w.a_rel, cA, q0, n, ws.act_c);
       ++*cx.launch_counter;
       STIF_TRY(cudaGetLastError());
@@ -522,7 +539,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
     // stage B
     for (long q0 = 0; q0 < Q; q0 += chunk) {
       long n = std::min(chunk, Q - q0);
-      unsigned blocks = (unsigned)((n * 64 + 255) / 256);
+      unsigned blocks = (unsigned)((n * 16 + 255) / 256);
       stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, ws.ftab, nullptr);
       ++*cx.launch_counter;
       STIF_TRY(cudaGetLastError());
