@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256, K == 64 ? 2 : 1) hp_gemm_kernel(const __g
 // terms, same order within an accumulator), so the two agree bit for bit.
 constexpr uint32_t kHp2StageA = 2 * 16384;   // A hi | A lo of one K block
 __host__ __device__ constexpr uint32_t hp2_stage_bytes(int N) { return kHp2StageA + 2u * (uint32_t)N * 128u; }
-__host__ __device__ constexpr uint32_t hp2_smem_bytes(int N) { return 2u * hp2_stage_bytes(N) + 128u; }
+__host__ __device__ constexpr uint32_t hp2_smem_bytes(int N) { return 2u * hp2_stage_bytes(N) + 128u + 8u * 4096u; }   // + one 32 x 32 fp32 transpose tile per epilogue warp
 
 __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant__ HpGemmParams p) {
   const int KB = p.K / 64, NC = p.N / 64;
@@ -190,26 +190,39 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
   if (warp < 8) {
     // ---------------- epilogue: thread = one row x half of the N columns
     const int quarter = warp & 3, ncol = p.N / 2, cbeg = (warp >> 2) * ncol;
+    float4* xpose = reinterpret_cast<float4*>(hp_smem + 2 * stage_bytes + 128) + warp * 256;
     long it = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t b = (uint32_t)(it & 1);
       wait_or_trap(&bars[4 + b], (uint32_t)(it >> 1) & 1);
       tc_fence_after();
-      const long row = tile * 128 + quarter * 32 + lane;
+      const long row0 = tile * 128 + quarter * 32;
       for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256u + (uint32_t)c0, v);
         tmem_ld_wait();
-        float o[32];
+        // thread = row holds 32 consecutive outputs: transposed through the warp's shared tile (16-byte slots XOR-swizzled by the row,
+        // 4 wavefronts per access both ways) so that every store instruction of the warp writes 4 rows x 128 contiguous bytes
+        // instead of 32 rows x 16 bytes (the row-per-thread stores of version 1 cost one L2 request per 16 bytes: 8.6 us per tile).
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float x = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + c0 + j) : 0.f);
-          o[j] = p.act ? hp_sin(x) : x;
+        for (int j = 0; j < 8; ++j) {
+          float4 o;
+          float* oe = reinterpret_cast<float*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = __uint_as_float(v[4 * j + e]) + (p.bias ? __ldg(p.bias + c0 + 4 * j + e) : 0.f);
+            oe[e] = p.act ? hp_sin(x) : x;
+          }
+          xpose[lane * 8 + (j ^ (lane & 7))] = o;
         }
-        if (row < p.M) {
-          float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + c0);
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int i = 0; i < 8; ++i) {
+          const int r = i * 4 + (lane >> 3), slot = lane & 7;
+          const float4 o = xpose[r * 8 + (slot ^ (r & 7))];
+          const long grow = row0 + r;
+          if (grow < p.M) *reinterpret_cast<float4*>(p.C + grow * p.ldc + c0 + slot * 4) = o;
         }
       }
       tc_fence_before();
