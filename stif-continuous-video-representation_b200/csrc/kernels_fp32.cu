@@ -461,6 +461,17 @@ static cudaError_t dense_layer(const LaunchCtx& cx, const DeviceWeights32& w, in
   return launch_gemm(cx, dense(A, K, Wt + (size_t)n_off * K, bias + n_off, C, ldc, M, N, act), false);
 }
 
+// A 256-wide sine layer followed by its NOUT-wide output layer: one launch on the tensor-core path (the activations stay in the
+// epilogue's registers, hp_gemm_proj), two on the SIMT anchor (through the scratch activations `act`).
+template <int NOUT>
+static cudaError_t dense_out_layer(const LaunchCtx& cx, const DeviceWeights32& w, int id, const float* A, int K, const float* Wt,
+                                   const float* bias, float* act, const float* out_w, const float* out_b, float* out, long scm, long scn,
+                                   long M) {
+  if (const HpLayer* L = hp_layer(w.hp, id)) return hp_gemm_proj(cx, *L, A, bias, M, out_w, out_b, NOUT, out, scm, scn);
+  STIF_TRY(dense_layer(cx, w, id, 0, 256, A, K, Wt, bias, act, 256, M, 1));
+  return launch_out_layer<NOUT>(cx, act, out_w, out_b, out, scm, scn, M);
+}
+
 cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
                              const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
                              int k1_row_end, float* out_rgb, int stage) {
@@ -486,8 +497,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(dense_layer(cx, w, HP_L1, 0, 64, ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 1));
-    STIF_TRY(dense_layer(cx, w, HP_L2, 0, 256, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 1));
-    STIF_TRY(launch_out_layer<4>(cx, ws.act_b, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, 1, n));
+    STIF_TRY((dense_out_layer<4>(cx, w, HP_L2, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, 1, n)));
   }
   // ---- K2: stage C + D + E over rows [row_begin, row_end)
   for (long q0 = row_begin * WW; stage == 2 && q0 < row_end * WW; q0 += chunk) {
@@ -499,8 +509,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(cudaGetLastError());
     STIF_TRY(dense_layer(cx, w, HP_E1, 0, 64, ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 1));
     STIF_TRY(dense_layer(cx, w, HP_E2, 0, 256, ws.act_a, 64, w.e2_w, w.e2_b, ws.act_b, 256, n, 1));
-    STIF_TRY(dense_layer(cx, w, HP_E3, 0, 256, ws.act_b, 256, w.e3_w, w.e3_b, ws.act_a, 256, n, 1));
-    STIF_TRY(launch_out_layer<3>(cx, ws.act_a, w.e4_w, w.e4_b, out_rgb + q0, 1, Qall, n));   // planar [3,HH,WW] (Sakuya_arch_test.py:457)
+    STIF_TRY((dense_out_layer<3>(cx, w, HP_E3, ws.act_b, 256, w.e3_w, w.e3_b, ws.act_a, w.e4_w, w.e4_b, out_rgb + q0, 1, Qall, n)));   // planar [3,HH,WW] (Sakuya_arch_test.py:457)
   }
   return cudaSuccess;
 }
@@ -544,8 +553,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
       ++*cx.launch_counter;
       STIF_TRY(cudaGetLastError());
       STIF_TRY(dense_layer(cx, w, HP_L1, 0, 64, ws.act_c, 64, w.l1_w, w.l1_b, ws.act_a, 64, n, 1));
-      STIF_TRY(dense_layer(cx, w, HP_L2, 0, 256, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, 256, n, 1));
-      STIF_TRY(launch_out_layer<4>(cx, ws.act_b, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, 1, n));
+      STIF_TRY((dense_out_layer<4>(cx, w, HP_L2, ws.act_a, 64, w.l2_w, w.l2_b, ws.act_b, w.l3_w, w.l3_b, ws.flow + q0 * 4, 4, 1, n)));
     }
     // stage C + D + E into the per-pass prediction, then the area-weighted accumulation
     STIF_TRY(decode_slab_fp32(cx, w, hw, geo, ws, t, 0, geo.HH, 0, geo.HH, ws.pred, 2));

@@ -35,7 +35,14 @@ struct HpGemmParams {
   float* C;                // [M, ldc]
   long ldc, M;
   int n_total, n_off, N, K;
-  int act;                 // 0 identity, 1 sinf
+  int act;                 // 0 identity, 1 sine
+  // version 2 only: the activations are not stored but contracted with an output layer proj_w [proj_n, 256] (+ proj_b) in the
+  // epilogue (the 256 -> 4 flow and 256 -> 3 RGB layers: saves writing and re-reading 1 KB per query); needs N == 256
+  const float* proj_w = nullptr;
+  const float* proj_b = nullptr;
+  float* proj_out = nullptr;   // out[m * proj_scm + j * proj_scn]
+  long proj_scm = 0, proj_scn = 0;
+  int proj_n = 0;
 };
 
 extern __shared__ __align__(1024) uint8_t hp_smem[];
@@ -191,12 +198,62 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
     // ---------------- epilogue: thread = one row x half of the N columns
     const int quarter = warp & 3, ncol = p.N / 2, cbeg = (warp >> 2) * ncol;
     float4* xpose = reinterpret_cast<float4*>(hp_smem + 2 * stage_bytes + 128) + warp * 256;
+    float4* pw = reinterpret_cast<float4*>(hp_smem + 2 * stage_bytes + 128);            // proj mode: proj_w [proj_n][256] ...
+    float4* pex = pw + 256;                                                                // ... and the partial-sum exchange [2][4][32]
+    if (p.proj_n) {
+      for (int i = tid; i < p.proj_n * 64; i += 256) pw[i] = __ldg(reinterpret_cast<const float4*>(p.proj_w) + i);
+      asm volatile("bar.sync 9, 256;" ::: "memory");   // the 8 epilogue warps
+    }
     long it = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t b = (uint32_t)(it & 1);
       wait_or_trap(&bars[4 + b], (uint32_t)(it >> 1) & 1);
       tc_fence_after();
       const long row0 = tile * 128 + quarter * 32;
+      if (p.proj_n) {
+        // thread = row x 128 of the 256 activations: partial dot products with the output layer, the two column halves (warps w
+        // and w + 4) meet in shared memory; nothing of the 256-wide activation ever reaches HBM
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256u + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[e] = hp_sin(__uint_as_float(v[4 * j + e]) + __ldg(p.bias + c0 + 4 * j + e));
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+              if (n < p.proj_n) {
+                const float4 w4 = pw[n * 64 + (c0 >> 2) + j];
+                acc[n] = fmaf(o[3], w4.w, fmaf(o[2], w4.z, fmaf(o[1], w4.y, fmaf(o[0], w4.x, acc[n]))));
+              }
+          }
+        }
+        tc_fence_before();
+        const int slot = ((int)b * 4 + quarter) * 32 + lane, barid = 1 + (int)b * 4 + quarter;
+        if (warp >= 4) {
+          pex[slot] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          __threadfence_block();
+          asm volatile("bar.arrive %0, 64;" ::"r"(barid) : "memory");
+        } else {
+          asm volatile("bar.sync %0, 64;" ::"r"(barid) : "memory");
+          const float4 o = pex[slot];
+          const long grow = row0 + lane;
+          if (grow < p.M) {
+            const float r[4] = {acc[0] + o.x, acc[1] + o.y, acc[2] + o.z, acc[3] + o.w};
+            if (p.proj_n == 4 && p.proj_scn == 1 && p.proj_scm == 4) {
+              *reinterpret_cast<float4*>(p.proj_out + grow * 4) =
+                  make_float4(r[0] + __ldg(p.proj_b), r[1] + __ldg(p.proj_b + 1), r[2] + __ldg(p.proj_b + 2), r[3] + __ldg(p.proj_b + 3));
+            } else {
+              for (int n = 0; n < p.proj_n; ++n) p.proj_out[grow * p.proj_scm + n * p.proj_scn] = r[n] + __ldg(p.proj_b + n);
+            }
+          }
+        }
+        mbar_arrive(&bars[6 + b]);
+        continue;
+      }
       for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + b * 256u + (uint32_t)c0, v);
@@ -371,6 +428,19 @@ cudaError_t hp_gemm(const LaunchCtx& cx, const HpLayer& L, int n_off, int N, con
   }
   if (L.K == 64) hp_gemm_kernel<64><<<grid, 256, hp_smem_bytes<64>(), cx.stream>>>(p);
   else hp_gemm_kernel<256><<<grid, 256, hp_smem_bytes<256>(), cx.stream>>>(p);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
+// act(A W^T + b) contracted with the NOUT x 256 output layer in the epilogue (version 2 kernel): out[m * scm + j * scn]
+cudaError_t hp_gemm_proj(const LaunchCtx& cx, const HpLayer& L, const float* A, const float* bias, long M, const float* proj_w,
+                         const float* proj_b, int proj_n, float* out, long scm, long scn) {
+  if (M <= 0) return cudaSuccess;
+  if (L.N != 256 || (L.K != 64 && L.K != 256) || proj_n < 1 || proj_n > 4 || !bias) return cudaErrorInvalidValue;
+  HpGemmParams p{A, L.hi, L.lo, bias, nullptr, 0, M, L.N, 0, 256, L.K, 1};
+  p.proj_w = proj_w; p.proj_b = proj_b; p.proj_out = out; p.proj_scm = scm; p.proj_scn = scn; p.proj_n = proj_n;
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  hp_gemm2_kernel<<<std::min<unsigned>(grid, (unsigned)cx.num_sms), 544, hp2_smem_bytes(256), cx.stream>>>(p);
   ++*cx.launch_counter;
   return cudaGetLastError();
 }
