@@ -126,7 +126,7 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode) {
     }
   }
   if (fp32) {
-    ws.chunk = std::min<size_t>(Q, (size_t)1 << 18);
+    ws.chunk = std::min<size_t>(Q, (size_t)1 << 20);   // queries per launch of the layer-by-layer pipeline (2.3 KB of activations each)
     ws.act_a = (float*)take(ws.chunk * 256 * sizeof(float));
     ws.act_b = (float*)take(ws.chunk * 256 * sizeof(float));
     ws.act_c = (float*)take(ws.chunk * 64 * sizeof(float));
