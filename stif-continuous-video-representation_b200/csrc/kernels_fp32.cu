@@ -461,6 +461,14 @@ static cudaError_t dense_layer(const LaunchCtx& cx, const DeviceWeights32& w, in
   return launch_gemm(cx, dense(A, K, Wt + (size_t)n_off * K, bias + n_off, C, ldc, M, N, act), false);
 }
 
+// The composed last layer of feat_imnet (256 -> F 64 | Q1 64 | Q2 64, no activation): F and Q1|Q2 live in different tables; one pass
+// over the 256-wide input on the tensor-core path (hp_gemm_split), two on the SIMT anchor.
+static cudaError_t composed_layer(const LaunchCtx& cx, const DeviceWeights32& w, const float* A, float* f_out, float* q_out, long M) {
+  if (const HpLayer* L = hp_layer(w.hp, HP_F3)) return hp_gemm_split(cx, *L, A, w.f3_b, M, 0, 64, f_out, 64, q_out, 128);
+  STIF_TRY(dense_layer(cx, w, HP_F3, 0, 64, A, 256, w.f3_w, w.f3_b, f_out, 64, M, 0));
+  return dense_layer(cx, w, HP_F3, 64, 128, A, 256, w.f3_w, w.f3_b, q_out, 128, M, 0);
+}
+
 // A 256-wide sine layer followed by its NOUT-wide output layer: one launch on the tensor-core path (the activations stay in the
 // epilogue's registers, hp_gemm_proj), two on the SIMT anchor (through the scratch activations `act`).
 template <int NOUT>
@@ -491,8 +499,7 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
     STIF_TRY(cudaGetLastError());
     STIF_TRY(dense_layer(cx, w, HP_F1, 0, 64, ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 1));
     STIF_TRY(dense_layer(cx, w, HP_F2, 0, 256, ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 1));
-    STIF_TRY(dense_layer(cx, w, HP_F3, 0, 64, ws.act_b, 256, w.f3_w, w.f3_b, ws.act_c, 64, n, 0));
-    STIF_TRY(dense_layer(cx, w, HP_F3, 64, 128, ws.act_b, 256, w.f3_w, w.f3_b, qtab + q0 * 128, 128, n, 0));
+    STIF_TRY(composed_layer(cx, w, ws.act_b, ws.act_c, qtab + q0 * 128, n));
     stage_b_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, geo, cB, q0, n, ws.act_c, nullptr, reinterpret_cast<const float*>(ws.utab));
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
@@ -542,8 +549,7 @@ cudaError_t decode_slab_fp32_ensemble(const LaunchCtx& cx, const DeviceWeights32
       STIF_TRY(cudaGetLastError());
       STIF_TRY(dense_layer(cx, w, HP_F1, 0, 64, ws.act_c, 64, w.f1_w, w.f1_b, ws.act_a, 64, n, 1));
       STIF_TRY(dense_layer(cx, w, HP_F2, 0, 256, ws.act_a, 64, w.f2_w, w.f2_b, ws.act_b, 256, n, 1));
-      STIF_TRY(dense_layer(cx, w, HP_F3, 0, 64, ws.act_b, 256, w.f3_w, w.f3_b, ws.ftab + q0 * 64, 64, n, 0));
-      STIF_TRY(dense_layer(cx, w, HP_F3, 64, 128, ws.act_b, 256, w.f3_w, w.f3_b, qtab + q0 * 128, 128, n, 0));
+      STIF_TRY(composed_layer(cx, w, ws.act_b, ws.ftab + q0 * 64, qtab + q0 * 128, n));
     }
     // stage B
     for (long q0 = 0; q0 < Q; q0 += chunk) {

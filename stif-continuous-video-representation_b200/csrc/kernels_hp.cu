@@ -38,6 +38,11 @@ struct HpGemmParams {
   int act;                 // 0 identity, 1 sine
   // version 2 only: the activations are not stored but contracted with an output layer proj_w [proj_n, 256] (+ proj_b) in the
   // epilogue (the 256 -> 4 flow and 256 -> 3 RGB layers: saves writing and re-reading 1 KB per query); needs N == 256
+  // version 2 only: output columns >= n_split go to C2[m * ldc2 + (col - n_split)] (the composed 256 -> 64 | 128 layer writes F
+  // and Q1|Q2 to different tables from ONE pass over its 256-wide input); n_split is a multiple of 32, 0 = no split
+  float* C2 = nullptr;
+  long ldc2 = 0;
+  int n_split = 0;
   const float* proj_w = nullptr;
   const float* proj_b = nullptr;
   float* proj_out = nullptr;   // out[m * proj_scm + j * proj_scn]
@@ -279,7 +284,10 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
           const int r = i * 4 + (lane >> 3), slot = lane & 7;
           const float4 o = xpose[r * 8 + (slot ^ (r & 7))];
           const long grow = row0 + r;
-          if (grow < p.M) *reinterpret_cast<float4*>(p.C + grow * p.ldc + c0 + slot * 4) = o;
+          if (grow < p.M) {
+            if (p.n_split && c0 >= p.n_split) *reinterpret_cast<float4*>(p.C2 + grow * p.ldc2 + (c0 - p.n_split) + slot * 4) = o;
+            else *reinterpret_cast<float4*>(p.C + grow * p.ldc + c0 + slot * 4) = o;
+          }
         }
       }
       tc_fence_before();
@@ -428,6 +436,19 @@ cudaError_t hp_gemm(const LaunchCtx& cx, const HpLayer& L, int n_off, int N, con
   }
   if (L.K == 64) hp_gemm_kernel<64><<<grid, 256, hp_smem_bytes<64>(), cx.stream>>>(p);
   else hp_gemm_kernel<256><<<grid, 256, hp_smem_bytes<256>(), cx.stream>>>(p);
+  ++*cx.launch_counter;
+  return cudaGetLastError();
+}
+
+// One pass over A, two destinations: columns [0, n_split) of the layer -> C, [n_split, L.N) -> C2 (version 2 kernel)
+cudaError_t hp_gemm_split(const LaunchCtx& cx, const HpLayer& L, const float* A, const float* bias, long M, int act, int n_split, float* C,
+                          long ldc, float* C2, long ldc2) {
+  if (M <= 0) return cudaSuccess;
+  if (L.N % 64 != 0 || L.N > 256 || n_split % 32 != 0 || n_split <= 0 || n_split >= L.N || ldc % 4 != 0 || ldc2 % 4 != 0) return cudaErrorInvalidValue;
+  HpGemmParams p{A, L.hi, L.lo, bias, C, ldc, M, L.N, 0, L.N, L.K, act};
+  p.C2 = C2; p.ldc2 = ldc2; p.n_split = n_split;
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  hp_gemm2_kernel<<<std::min<unsigned>(grid, (unsigned)cx.num_sms), 544, hp2_smem_bytes(L.N), cx.stream>>>(p);
   ++*cx.launch_counter;
   return cudaGetLastError();
 }

@@ -154,6 +154,9 @@ void hp_weights_destroy(HpWeights*);
 const HpLayer* hp_layer(const HpWeights* w, int id);
 cudaError_t hp_gemm(const LaunchCtx& cx, const HpLayer& L, int n_off, int N, const float* A, const float* bias, float* C, long ldc,
                     long M, int act);
+// ... with two destinations: columns [0, n_split) -> C, the rest -> C2
+cudaError_t hp_gemm_split(const LaunchCtx& cx, const HpLayer& L, const float* A, const float* bias, long M, int act, int n_split, float* C,
+                          long ldc, float* C2, long ldc2);
 // ... with the 256-wide sine activations contracted with a proj_n x 256 output layer in the epilogue instead of being stored
 cudaError_t hp_gemm_proj(const LaunchCtx& cx, const HpLayer& L, const float* A, const float* bias, long M, const float* proj_w,
                          const float* proj_b, int proj_n, float* out, long scm, long scn);
