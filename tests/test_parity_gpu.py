@@ -688,3 +688,31 @@ def test_projected_tables_saturate_instead_of_overflowing(stif):
     rgb = _run(dec, lat, fr, [0.5], None)
     dec.close()
     assert np.isfinite(rgb).all()
+
+
+def test_fp32_mode_gemm_backends_agree(tmp_path):
+    """STIF_MODE_FP32's dense layers have three back-ends: the persistent split-bf16 tcgen05 GEMM (default), the first one-tile-per-CTA
+    tensor-core kernel (STIF_HP_V1=1) and the SIMT SGEMM anchor (STIF_FP32_SIMT=1; plain fp32 FMAs, libdevice sinf).  The switches are
+    read when the library loads weights, so each runs in its own process on the same seeded inputs (odd sizes, two timesteps, stress
+    weights): the tensor-core paths must sit within 3e-5 of the anchor and within 1e-5 of each other."""
+    import subprocess
+    import sys
+    script = (
+        "import sys, numpy as np, torch\n"
+        f"sys.path.insert(0, {os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'stif-continuous-video-representation_b200')!r})\n"
+        "import stif_b200\n"
+        "from stif_b200 import synthetic as synth\n"
+        "dec = stif_b200.STIFQueryDecoder(0, mode='fp32'); dec.load_weights(synth.make_weights(4, True))\n"
+        "lat, fr = synth.make_inputs(21, 1, 37, 53, 0.3)\n"
+        "out = dec.decode_stacked(torch.from_numpy(lat).cuda(), torch.from_numpy(fr).cuda(), [0.25, 0.8], (301, 197))\n"
+        "np.save(sys.argv[1], out.cpu().numpy())\n")
+    outs = {}
+    for name, env in (("v2", {}), ("v1", {"STIF_HP_V1": "1"}), ("simt", {"STIF_FP32_SIMT": "1"})):
+        path = str(tmp_path / f"{name}.npy")
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=dict(os.environ, **env), timeout=600)
+        outs[name] = np.load(path)
+    assert np.isfinite(outs["simt"]).all() and np.abs(outs["simt"]).max() > 0.05
+    d_anchor = max(np.abs(outs["v2"] - outs["simt"]).max(), np.abs(outs["v1"] - outs["simt"]).max())
+    d_tc = np.abs(outs["v2"] - outs["v1"]).max()
+    print(f"fp32 back-ends: tensor-core vs SIMT anchor {d_anchor:.3e}, v2 vs v1 {d_tc:.3e}")
+    assert d_anchor <= 3e-5 and d_tc <= 1e-5
