@@ -65,6 +65,14 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
     if (it > (1u << 24)) __trap();
 }
+// the roles of the persistent GEMM wait for microseconds at a time: back off so that the spinning warps leave the issue slots to
+// the epilogue (the spin loops were 18 % of the executed instructions)
+__device__ __forceinline__ void wait_backoff_or_trap(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > 4) __nanosleep(it < 64 ? 40 : 200);
+    if (it > (1u << 22)) __trap();
+  }
+}
 
 template <int K>
 __global__ void __launch_bounds__(256, K == 64 ? 2 : 1) hp_gemm_kernel(const __grid_constant__ HpGemmParams p) {
@@ -173,7 +181,7 @@ __global__ void __launch_bounds__(256, K == 64 ? 2 : 1) hp_gemm_kernel(const __g
 // terms, same order within an accumulator), so the two agree bit for bit.
 constexpr uint32_t kHp2StageA = 2 * 16384;   // A hi | A lo of one K block
 __host__ __device__ constexpr uint32_t hp2_stage_bytes(int N) { return kHp2StageA + 2u * (uint32_t)N * 128u; }
-__host__ __device__ constexpr uint32_t hp2_smem_bytes(int N) { return 2u * hp2_stage_bytes(N) + 128u + 8u * 4096u; }   // + one 32 x 32 fp32 transpose tile per epilogue warp
+__host__ __device__ constexpr uint32_t hp2_smem_bytes(int N) { return 2u * hp2_stage_bytes(N) + 128u + 8u * 4096u + 1024u; }   // + one 32 x 32 fp32 transpose tile per epilogue warp + the layer's bias
 
 __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant__ HpGemmParams p) {
   const int KB = p.K / 64, NC = p.N / 64;
@@ -205,14 +213,16 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
     float4* xpose = reinterpret_cast<float4*>(hp_smem + 2 * stage_bytes + 128) + warp * 256;
     float4* pw = reinterpret_cast<float4*>(hp_smem + 2 * stage_bytes + 128);            // proj mode: proj_w [proj_n][256] ...
     float4* pex = pw + 256;                                                                // ... and the partial-sum exchange [2][4][32]
-    if (p.proj_n) {
+    // the bias in shared memory: a per-element __ldg sat on every accumulator's dependency chain (16 % of the stall samples)
+    float* sbias = reinterpret_cast<float*>(hp_smem + 2 * stage_bytes + 128 + 8 * 4096);
+    for (int i = tid; i < p.N; i += 256) sbias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    if (p.proj_n)
       for (int i = tid; i < p.proj_n * 64; i += 256) pw[i] = __ldg(reinterpret_cast<const float4*>(p.proj_w) + i);
-      asm volatile("bar.sync 9, 256;" ::: "memory");   // the 8 epilogue warps
-    }
+    asm volatile("bar.sync 9, 256;" ::: "memory");   // the 8 epilogue warps
     long it = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t b = (uint32_t)(it & 1);
-      wait_or_trap(&bars[4 + b], (uint32_t)(it >> 1) & 1);
+      wait_backoff_or_trap(&bars[4 + b], (uint32_t)(it >> 1) & 1);
       tc_fence_after();
       const long row0 = tile * 128 + quarter * 32;
       if (p.proj_n) {
@@ -227,7 +237,9 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
           for (int j = 0; j < 8; ++j) {
             float o[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) o[e] = hp_sin(__uint_as_float(v[4 * j + e]) + __ldg(p.bias + c0 + 4 * j + e));
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+            o[0] = hp_sin(__uint_as_float(v[4 * j]) + b4.x); o[1] = hp_sin(__uint_as_float(v[4 * j + 1]) + b4.y);
+            o[2] = hp_sin(__uint_as_float(v[4 * j + 2]) + b4.z); o[3] = hp_sin(__uint_as_float(v[4 * j + 3]) + b4.w);
 #pragma unroll
             for (int n = 0; n < 4; ++n)
               if (n < p.proj_n) {
@@ -269,13 +281,10 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 o;
-          float* oe = reinterpret_cast<float*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float x = __uint_as_float(v[4 * j + e]) + (p.bias ? __ldg(p.bias + c0 + 4 * j + e) : 0.f);
-            oe[e] = p.act ? hp_sin(x) : x;
-          }
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
+          float4 o = make_float4(__uint_as_float(v[4 * j]) + b4.x, __uint_as_float(v[4 * j + 1]) + b4.y,
+                                 __uint_as_float(v[4 * j + 2]) + b4.z, __uint_as_float(v[4 * j + 3]) + b4.w);
+          if (p.act) o = make_float4(hp_sin(o.x), hp_sin(o.y), hp_sin(o.z), hp_sin(o.w));
           xpose[lane * 8 + (j ^ (lane & 7))] = o;
         }
         __syncwarp();
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
       for (int kb = 0; kb < KB; ++kb, ++item) {
         const uint32_t s = (uint32_t)(item & 1);
         if (s != group) continue;
-        wait_or_trap(&bars[2 + s], ((uint32_t)(item >> 1) & 1) ^ 1);   // (passes at once the first time round)
+        wait_backoff_or_trap(&bars[2 + s], ((uint32_t)(item >> 1) & 1) ^ 1);   // (passes at once the first time round)
         uint8_t* st = hp_smem + s * stage_bytes;
         if (pt == 0) {
           mbar_arrive_expect_tx(&bars[s], 2 * w_bytes);
