@@ -442,12 +442,49 @@ cudaError_t project_frames_up4(const LaunchCtx& cx, const DeviceWeights32& w, co
   return cudaGetLastError();
 }
 
+// [latent(192); frames(6)] for texels [m0, m0 + n), channel-major in the reference's layout, as row-major [n, 256] rows (columns 198..255
+// zero): what the tensor-core GEMM reads.  32 x 32 tiles through shared memory, coalesced both ways.
+__global__ void pack_latent_rows_kernel(const float* __restrict__ latent, const float* __restrict__ frames, long HW, long m0, long n,
+                                        float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long m = (long)blockIdx.x * 32 + tx;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ch = blockIdx.y * 32 + ty + 8 * i;
+    float v = 0.f;
+    if (m < n) {
+      if (ch < 192) v = __ldg(latent + (long)ch * HW + m0 + m);
+      else if (ch < 198) v = __ldg(frames + (long)(ch - 192) * HW + m0 + m);
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long row = (long)blockIdx.x * 32 + ty + 8 * i;
+    if (row < n) out[row * 256 + blockIdx.y * 32 + tx] = tile[tx][ty + 8 * i];
+  }
+}
+
 cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
-                           int H, int W, void* tab, bool tab_half, bool test_variant) {
+                           int H, int W, void* tab, bool tab_half, bool test_variant, float* scratch, size_t scratch_rows) {
+  const long HW = (long)H * W;
+  const HpLayer* L = hp_layer(w.hp, test_variant ? HP_K0T : HP_K0);
+  if (L && scratch && scratch_rows >= 128 && !tab_half) {   // tensor cores (split-bf16): 1.0 -> ~0.25 ms per 270 x 480 pair
+    for (long m0 = 0; m0 < HW; m0 += (long)scratch_rows) {
+      const long n = std::min<long>((long)scratch_rows, HW - m0);
+      pack_latent_rows_kernel<<<dim3((unsigned)((n + 31) / 32), 8), dim3(32, 8), 0, cx.stream>>>(latent192, frames6, HW, m0, n, scratch);
+      ++*cx.launch_counter;
+      if (cudaError_t e = cudaGetLastError()) return e;
+      if (cudaError_t e = hp_gemm(cx, *L, 0, 256, scratch, nullptr, (float*)tab + m0 * 256, 256, n, 0)) return e;
+    }
+    return cudaSuccess;
+  }
   GemmArgs g{};
-  g.A = latent192; g.A2 = frames6; g.sam = 1; g.sak = (long)H * W; g.ksplit = 192;
+  g.A = latent192; g.A2 = frames6; g.sam = 1; g.sak = HW; g.ksplit = 192;
   g.Wt = test_variant ? w.w_tab_lat : w.w_tab; g.bias = nullptr; g.C = tab; g.scm = 256; g.scn = 1;
-  g.M = (long)H * W; g.N = 256; g.K = 198; g.act = 0; g.out_half = tab_half ? 1 : 0;
+  g.M = HW; g.N = 256; g.K = 198; g.act = 0; g.out_half = tab_half ? 1 : 0;
   return launch_gemm(cx, g, true);
 }
 

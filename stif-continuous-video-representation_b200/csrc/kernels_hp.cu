@@ -388,17 +388,24 @@ void split_images(const std::vector<float>& w, int N, int K, std::vector<uint8_t
 }  // namespace
 
 struct HpWeights {
-  HpLayer layer[8];
+  HpLayer layer[HP_NUM_LAYERS];
 };
 
 const HpLayer* hp_layer(const HpWeights* w, int id) { return w ? &w->layer[id] : nullptr; }
 
 HpWeights* hp_weights_create(const FoldedWeights& hw, std::string& err) {
   auto* t = new HpWeights();
-  const std::vector<float>* src[8] = {&hw.f1_w, &hw.f2_w, &hw.f3_w, &hw.l1_w, &hw.l2_w, &hw.e1_w, &hw.e2_w, &hw.e3_w};
-  const int N[8] = {64, 256, 192, 64, 256, 64, 256, 256}, K[8] = {64, 64, 256, 64, 64, 64, 64, 256};
-  for (int i = 0; i < 8; ++i) t->layer[i] = HpLayer{nullptr, nullptr, N[i], K[i]};
-  for (int i = 0; i < 8; ++i) {
+  // the projection's [256, 198] matrices padded to K = 256 with zero columns (the packed input rows carry zeros there too)
+  std::vector<float> k0[2] = {std::vector<float>((size_t)256 * 256, 0.f), std::vector<float>((size_t)256 * 256, 0.f)};
+  for (int r = 0; r < 256; ++r)
+    for (int c = 0; c < 198; ++c) {
+      k0[0][(size_t)r * 256 + c] = hw.w_tab[(size_t)r * 198 + c];
+      k0[1][(size_t)r * 256 + c] = hw.w_tab_lat[(size_t)r * 198 + c];
+    }
+  const std::vector<float>* src[HP_NUM_LAYERS] = {&hw.f1_w, &hw.f2_w, &hw.f3_w, &hw.l1_w, &hw.l2_w, &hw.e1_w, &hw.e2_w, &hw.e3_w, &k0[0], &k0[1]};
+  const int N[HP_NUM_LAYERS] = {64, 256, 192, 64, 256, 64, 256, 256, 256, 256}, K[HP_NUM_LAYERS] = {64, 64, 256, 64, 64, 64, 64, 256, 256, 256};
+  for (int i = 0; i < HP_NUM_LAYERS; ++i) t->layer[i] = HpLayer{nullptr, nullptr, N[i], K[i]};
+  for (int i = 0; i < HP_NUM_LAYERS; ++i) {
     std::vector<uint8_t> hi, lo;
     split_images(*src[i], N[i], K[i], hi, lo);
     cudaError_t e = cudaMalloc(&t->layer[i].hi, hi.size());

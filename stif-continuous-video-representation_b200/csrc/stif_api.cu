@@ -570,7 +570,7 @@ int decode_impl(stif_decoder* d, const float* latent, const float* frames, int B
         }
       }
       else if (k == nbands - 1) {
-        CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false, test_variant));
+        CUDA_OR_RETURN(project_latent(cx, d->w32, lat_b, fr_b, H, W, ws.tab, false, test_variant, ws.act_a, ws.chunk));
         if (test_variant) CUDA_OR_RETURN(project_frames_up4(cx, d->w32, fr_b, H, W, (float*)ws.utab));
       }
     }

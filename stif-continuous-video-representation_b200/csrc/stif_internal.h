@@ -40,7 +40,7 @@ void fold_weights(const float* const* tensors, FoldedWeights& out);
 // Split-bf16 tensor-core GEMMs of the high-precision mode (kernels_hp.cu): per dense layer the bf16 hi / lo SW128 images.
 struct HpLayer { uint8_t* hi; uint8_t* lo; int N, K; };
 struct HpWeights;
-enum HpLayerId { HP_F1 = 0, HP_F2, HP_F3, HP_L1, HP_L2, HP_E1, HP_E2, HP_E3 };
+enum HpLayerId { HP_F1 = 0, HP_F2, HP_F3, HP_L1, HP_L2, HP_E1, HP_E2, HP_E3, HP_K0, HP_K0T, HP_NUM_LAYERS };   // K0 / K0T: the projection (K = 198 padded to 256), plain / decoding_test
 
 // Device-side view of the fp32 copy (kernels_fp32.cu).
 struct DeviceWeights32 {
@@ -94,8 +94,10 @@ Workspace carve_workspace(void* base, int H, int W, int HH, int WW, int mode);
 // fp32 FMA-pipe path (kernels_fp32.cu)
 // decoding_test variant (Sakuya_arch_test.py:513-514): utab[4H*4W,192] = w_up . bilinear_upsample_x4(frames)
 cudaError_t project_frames_up4(const LaunchCtx& cx, const DeviceWeights32& w, const float* frames6, int H, int W, float* utab);
+// scratch (optional): [scratch_rows, 256] fp32 for the row-major copy of [latent; frames] the tensor-core projection reads
 cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const float* latent192, const float* frames6,
-                           int H, int W, void* tab, bool tab_half, bool test_variant = false);
+                           int H, int W, void* tab, bool tab_half, bool test_variant = false, float* scratch = nullptr,
+                           size_t scratch_rows = 0);
 cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, const FoldedWeights& hw, const Geometry& geo,
                              const Workspace& ws, float t, int row_begin, int row_end, int k1_row_begin,
                              int k1_row_end, float* out_rgb /* [3,HH,WW] */, int stage /* 1 = K1 (A+B), 2 = K2 (C+D+E) */);
