@@ -285,6 +285,43 @@ __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* 
   reinterpret_cast<float4*>(out)[i] = sin4(s);
 }
 
+// The same without the upsampled-frame terms (every decode except decoding_test), with the tap arithmetic shared: the 16 lanes of a
+// query each derive ONE of its 16 taps (2 warps x {HR, LR} x 4 corners) and the (offset, weight) pairs travel by shuffle, in the
+// accumulation order of the kernel above (bit-identical result, ~3x fewer instructions).
+__global__ void stage_e_first_layer_shfl(const float* __restrict__ tab, const float* __restrict__ qtab,
+                                         const float* __restrict__ flow, Geometry g, Vec64 cst, long q0, long n,
+                                         int band_lo, int band_hi, int* __restrict__ flag, float* __restrict__ out) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n * 16;                     // (whole 16-lane groups are live or not: n * 16 is a multiple of 16)
+  const int l16 = threadIdx.x & 15, c = l16 * 4;
+  const long q = q0 + (live ? (i >> 4) : 0);
+  const int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  const float4 fl = reinterpret_cast<const float4*>(flow)[q];
+  const int wv = l16 >> 3, kind = (l16 >> 2) & 1, k = l16 & 3;
+  float gy, gx;
+  warp_position(g, jy, jx, wv == 0 ? fl.x : fl.z, wv == 0 ? fl.y : fl.w, gy, gx);
+  const Taps t = kind ? make_taps(gy, gx, g.H, g.W) : make_taps(gy, gx, g.HH, g.WW);
+  int my_off = k == 0 ? t.off[0] : k == 1 ? t.off[1] : k == 2 ? t.off[2] : t.off[3];
+  float my_w = k == 0 ? t.w[0] : k == 1 ? t.w[1] : k == 2 ? t.w[2] : t.w[3];
+  if (kind == 0 && my_w != 0.f) {                   // HR tap: must lie in the rows stage A+B has produced (see the kernel above)
+    const int row = my_off / g.WW;
+    if (row < band_lo || row >= band_hi) { if (live) atomicOr(flag, 1); my_w = 0.f; }
+  }
+  float4 s = make_float4(cst.v[c], cst.v[c + 1], cst.v[c + 2], cst.v[c + 3]);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const int off = __shfl_sync(0xffffffffu, my_off, j, 16);
+    const float w = __shfl_sync(0xffffffffu, my_w, j, 16);
+    const int jwv = j >> 3, jkind = (j >> 2) & 1;
+    if (jkind == 0) {
+      if (w != 0.f) fma4(w, ld4(qtab + (long)off * 128 + jwv * 64 + c), s);
+    } else {
+      fma4(w, ld4(tab + (long)off * 256 + 128 + jwv * 64 + c), s);
+    }
+  }
+  if (live) reinterpret_cast<float4*>(out)[i] = sin4(s);
+}
+
 Vec64 time_constant(const std::vector<float>& wt, const std::vector<float>& b, float t) {
   Vec64 v;
   for (int c = 0; c < 64; ++c) v.v[c] = wt[c] * t + b[c];
@@ -547,8 +584,11 @@ cudaError_t decode_slab_fp32(const LaunchCtx& cx, const DeviceWeights32& w, cons
   for (long q0 = row_begin * WW; stage == 2 && q0 < row_end * WW; q0 += chunk) {
     long n = std::min(chunk, row_end * WW - q0);
     unsigned blocks = (unsigned)((n * 16 + 255) / 256);
-    stage_e_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end,
-                                                      ws.flag, ws.act_c, reinterpret_cast<const float*>(ws.utab));
+    if (ws.utab)
+      stage_e_first_layer<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end,
+                                                        ws.flag, ws.act_c, reinterpret_cast<const float*>(ws.utab));
+    else
+      stage_e_first_layer_shfl<<<blocks, 256, 0, cx.stream>>>(tab, qtab, ws.flow, geo, cE, q0, n, k1_row_begin, k1_row_end, ws.flag, ws.act_c);
     ++*cx.launch_counter;
     STIF_TRY(cudaGetLastError());
     STIF_TRY(dense_layer(cx, w, HP_E1, 0, 64, ws.act_c, 64, w.e1_w, w.e1_b, ws.act_a, 64, n, 1));

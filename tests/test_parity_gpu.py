@@ -694,7 +694,7 @@ def test_fp32_mode_gemm_backends_agree(tmp_path):
     """STIF_MODE_FP32's dense layers have three back-ends: the persistent split-bf16 tcgen05 GEMM (default), the first one-tile-per-CTA
     tensor-core kernel (STIF_HP_V1=1) and the SIMT SGEMM anchor (STIF_FP32_SIMT=1; plain fp32 FMAs, libdevice sinf).  The switches are
     read when the library loads weights, so each runs in its own process on the same seeded inputs (odd sizes, two timesteps, stress
-    weights): the tensor-core paths must sit within 3e-5 of the anchor and within 1e-5 of each other."""
+    weights): the tensor-core paths must sit within 3e-5 of the anchor and within 2e-5 of each other."""
     import subprocess
     import sys
     script = (
@@ -715,4 +715,4 @@ def test_fp32_mode_gemm_backends_agree(tmp_path):
     d_anchor = max(np.abs(outs["v2"] - outs["simt"]).max(), np.abs(outs["v1"] - outs["simt"]).max())
     d_tc = np.abs(outs["v2"] - outs["v1"]).max()
     print(f"fp32 back-ends: tensor-core vs SIMT anchor {d_anchor:.3e}, v2 vs v1 {d_tc:.3e}")
-    assert d_anchor <= 3e-5 and d_tc <= 1e-5
+    assert d_anchor <= 3e-5 and d_tc <= 2e-5
