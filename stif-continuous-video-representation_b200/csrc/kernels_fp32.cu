@@ -8,6 +8,7 @@
 //
 // Reference semantics: LunaTokis.decoding, codes/models/modules/Sakuya_arch_test.py:364-459.
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 
@@ -480,6 +481,88 @@ cudaError_t project_frames_up4(const LaunchCtx& cx, const DeviceWeights32& w, co
   return cudaGetLastError();
 }
 
+// ---- the projection K0 of the fp32 mode --------------------------------------------------------------------------------------
+// tab[m, n] = sum_k X[k, m] W[n, k] with X = [latent(192); frames(6)] in the reference's channel-major layout (row stride HW) and
+// W [256, 198]: exact fp32 FMAs in ascending k (the same rounding sequence as sgemm_bias_act_kernel, so the tables are bit-identical
+// to the anchor's), as a register-tiled SGEMM: 128 x 128 tile per 256-thread block, 8 x 8 outputs per thread in two 4-wide strips per
+// axis (conflict-free LDS.128), K in steps of 8 with the next step's global loads in flight under the FMAs.  ~3x the generic kernel.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k0_sgemm_kernel(const float* __restrict__ lat, const float* __restrict__ frames,
+                                                       const float* __restrict__ W, float* __restrict__ C, long HW) {
+  constexpr int K = 198, KT = 8, NK = (K + KT - 1) / KT;
+  __shared__ __align__(16) float As[2][KT][128];
+  __shared__ __align__(16) float Bs[2][KT][128];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const long m0 = (long)blockIdx.x * 128;
+  const int n0 = blockIdx.y * 128;
+  const int ak = t >> 5, am = (t & 31) * 4;          // A: one float4 (4 texels of channel k0 + ak) per thread
+  const int bn = t >> 1, bk = (t & 1) * 4;           // B: W[n0 + bn][k0 + bk .. +3]
+  auto load_a = [&](int k0) {
+    const int k = k0 + ak;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < K) {
+      const float* src = (k < 192 ? lat + (long)k * HW : frames + (long)(k - 192) * HW) + m0 + am;
+      if (VEC) {
+        if (m0 + am + 3 < HW) v = __ldg(reinterpret_cast<const float4*>(src));
+        else {
+          if (m0 + am < HW) v.x = __ldg(src);
+          if (m0 + am + 1 < HW) v.y = __ldg(src + 1);
+          if (m0 + am + 2 < HW) v.z = __ldg(src + 2);
+        }
+      } else {
+        if (m0 + am < HW) v.x = __ldg(src);
+        if (m0 + am + 1 < HW) v.y = __ldg(src + 1);
+        if (m0 + am + 2 < HW) v.z = __ldg(src + 2);
+        if (m0 + am + 3 < HW) v.w = __ldg(src + 3);
+      }
+    }
+    return v;
+  };
+  auto load_b = [&](int k0, float (&w)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = (k0 + bk + j < K) ? __ldg(W + (long)(n0 + bn) * K + k0 + bk + j) : 0.f;
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 a_next = load_a(0);
+  float b_next[4];
+  load_b(0, b_next);
+  for (int step = 0; step < NK; ++step) {
+    const int buf = step & 1;
+    *reinterpret_cast<float4*>(&As[buf][ak][am]) = a_next;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Bs[buf][bk + j][bn] = b_next[j];
+    __syncthreads();                                   // (two buffers: the stores of step s + 1 cannot overtake the reads of step s - 1's ... see below)
+    if (step + 1 < NK) {
+      a_next = load_a((step + 1) * KT);
+      load_b((step + 1) * KT, b_next);
+    }
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]), a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]), b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    // a block-wide barrier per step is enough with two buffers: buffer `buf` is next written at step + 2, after the barrier of step + 1,
+    // which every thread reaches only after finishing the reads above
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= HW) continue;
+    float* dst = C + m * 256 + n0;
+    *reinterpret_cast<float4*>(dst + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    *reinterpret_cast<float4*>(dst + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+  }
+}
+
 // [latent(192); frames(6)] for texels [m0, m0 + n), channel-major in the reference's layout, as row-major [n, 256] rows (columns 198..255
 // zero): what the tensor-core GEMM reads.  32 x 32 tiles through shared memory, coalesced both ways.
 __global__ void pack_latent_rows_kernel(const float* __restrict__ latent, const float* __restrict__ frames, long HW, long m0, long n,
@@ -523,6 +606,15 @@ cudaError_t project_latent(const LaunchCtx& cx, const DeviceWeights32& w, const 
       if (cudaError_t e = hp_gemm(cx, *L, 0, 256, scratch, nullptr, (float*)tab + m0 * 256, 256, n, 0)) return e;
     }
     return cudaSuccess;
+  }
+  if (!tab_half && w.hp) {   // (the SIMT anchor, STIF_FP32_SIMT=1, keeps the generic kernel below: same bits, a third of the speed)
+    const dim3 grid((unsigned)((HW + 127) / 128), 2);
+    const float* Wt = test_variant ? w.w_tab_lat : w.w_tab;
+    const bool vec = HW % 4 == 0 && (reinterpret_cast<uintptr_t>(latent192) & 15) == 0 && (reinterpret_cast<uintptr_t>(frames6) & 15) == 0;
+    if (vec) k0_sgemm_kernel<true><<<grid, 256, 0, cx.stream>>>(latent192, frames6, Wt, (float*)tab, HW);
+    else k0_sgemm_kernel<false><<<grid, 256, 0, cx.stream>>>(latent192, frames6, Wt, (float*)tab, HW);
+    ++*cx.launch_counter;
+    return cudaGetLastError();
   }
   GemmArgs g{};
   g.A = latent192; g.A2 = frames6; g.sam = 1; g.sak = HW; g.ksplit = 192;
