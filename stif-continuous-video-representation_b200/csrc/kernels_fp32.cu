@@ -162,6 +162,13 @@ struct Vec64 { float v[64]; };
 // reference: Sakuya_arch_test.py:382-400 (nearest gathers, rel_coord, pe_coord, first SineLayer).
 // (first-layer kernels: thread = (query, 4 consecutive channels) -- 16 threads share a query's index / tap arithmetic instead of
 // 64, every table access is one 16-byte load; the sine is tc::reduced_sin as in the dense layers' epilogues)
+// raster index -> (row, column): rasters have at most 2^30 pixels (check_shape), so one 32-bit division instead of two 64-bit ones
+// (which were most of these kernels' instructions)
+__device__ __forceinline__ void raster_pos(long q, int WW, int& jy, int& jx) {
+  const uint32_t qq = (uint32_t)q, w = (uint32_t)WW, y = qq / w;
+  jy = (int)y;
+  jx = (int)(qq - y * w);
+}
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void fma4(float w, const float4 v, float4& s) {
   s.x = fmaf(w, v.x, s.x); s.y = fmaf(w, v.y, s.y); s.z = fmaf(w, v.z, s.z); s.w = fmaf(w, v.w, s.w);
@@ -175,7 +182,8 @@ __global__ void stage_a_first_layer(const float* __restrict__ tab, Geometry g, c
   if (i >= n * 16) return;
   int c = (int)(i & 15) * 4;
   long q = q0 + (i >> 4);
-  int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  int jy, jx;
+  raster_pos(q, g.WW, jy, jx);
   int iy = g.y.idx[jy], ix = g.x.idx[jx];
   float4 ta = make_float4(0.f, 0.f, 0.f, 0.f);
   if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) ta = ld4(tab + ((long)iy * g.W + ix) * 256 + c);
@@ -207,7 +215,8 @@ __global__ void stage_b_first_layer(const float* __restrict__ tab, Geometry g, V
   if (i >= n * 16) return;
   int c = (int)(i & 15) * 4;
   long q = q0 + (i >> 4);
-  int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  int jy, jx;
+  raster_pos(q, g.WW, jy, jx);
   Taps tp = make_taps_tables(g, jy, jx);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -257,7 +266,8 @@ __global__ void stage_e_first_layer(const float* __restrict__ tab, const float* 
   if (i >= n * 16) return;
   int c = (int)(i & 15) * 4;
   long q = q0 + (i >> 4);
-  int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  int jy, jx;
+  raster_pos(q, g.WW, jy, jx);
   float4 fl = reinterpret_cast<const float4*>(flow)[q];
   float4 s = make_float4(cst.v[c], cst.v[c + 1], cst.v[c + 2], cst.v[c + 3]);
 #pragma unroll
@@ -297,7 +307,8 @@ __global__ void stage_e_first_layer_shfl(const float* __restrict__ tab, const fl
   const bool live = i < n * 16;                     // (whole 16-lane groups are live or not: n * 16 is a multiple of 16)
   const int l16 = threadIdx.x & 15, c = l16 * 4;
   const long q = q0 + (live ? (i >> 4) : 0);
-  const int jy = (int)(q / g.WW), jx = (int)(q % g.WW);
+  int jy, jx;
+  raster_pos(q, g.WW, jy, jx);
   const float4 fl = reinterpret_cast<const float4*>(flow)[q];
   const int wv = l16 >> 3, kind = (l16 >> 2) & 1, k = l16 & 3;
   float gy, gx;
