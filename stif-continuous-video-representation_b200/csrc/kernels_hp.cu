@@ -236,7 +236,6 @@ __global__ void __launch_bounds__(544, 1) hp_gemm2_kernel(const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float o[4];
-#pragma unroll
             const float4 b4 = *reinterpret_cast<const float4*>(sbias + c0 + 4 * j);
             o[0] = hp_sin(__uint_as_float(v[4 * j]) + b4.x); o[1] = hp_sin(__uint_as_float(v[4 * j + 1]) + b4.y);
             o[2] = hp_sin(__uint_as_float(v[4 * j + 2]) + b4.z); o[3] = hp_sin(__uint_as_float(v[4 * j + 3]) + b4.w);
