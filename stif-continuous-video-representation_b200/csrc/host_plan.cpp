@@ -21,7 +21,6 @@ HostBandPlan plan_host_bands(int H, int W, int HH, int WW, int G, int bands_hint
   const long slots = num_sms;
   auto k1_tiles = [&](int rows) { return ((long)rows * WW + 127) / 128; };
   auto k2_tiles = [&](int rows) { return (long)((rows + 7) / 8) * ((WW + 15) / 16); };
-  auto both_tiles = [&](int rows) { return std::max(k1_tiles(rows), k2_tiles(rows)); };
   auto wave_aligned = [&](int target, int step, auto tiles_of) {
     int best = std::max(step, target / step * step);
     double best_eff = 0.0;

@@ -290,6 +290,7 @@ struct SineTurn {
 #ifndef STIF_WAIT_MODE
 #define STIF_WAIT_MODE 0
 #endif
+#if STIF_WAIT_MODE == 1
 __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
   uint32_t ok;
   asm volatile(
@@ -301,6 +302,7 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+#endif
 __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the warp in hardware for a bounded time, so this loop turns only a few times per wait; the
   // iteration cap converts a lost arrival into a launch failure instead of a hung GPU.
@@ -326,11 +328,14 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
 #define STIF_LONG_WAIT_NS 0
 #endif
 __device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
-  if (STIF_LONG_WAIT_NS == 0) { mbar_wait_or_trap(bar, parity); return; }
+#if STIF_LONG_WAIT_NS == 0
+  mbar_wait_or_trap(bar, parity);
+#else
   for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
     __nanosleep(STIF_LONG_WAIT_NS);
     if (it > (1u << 22)) __trap();
   }
+#endif
 }
 
 __device__ __forceinline__ bool elect_one() {
